@@ -1,0 +1,104 @@
+"""Import the reference's own Python, unmodified, from /root/reference (TEST INFRASTRUCTURE ONLY).
+
+Only usable in the build container (the reference tree does not travel to the GPU box); used by
+``tests/golden/make_golden.py`` to freeze golden vectors and by the optional
+``tests/test_oracle_vs_reference.py`` (skipped when the tree is absent).
+
+* classification: ``custom.py`` imports directly (deps: torch / numpy / scipy).
+* mmdet: ``losses/{utils,accuracy,cross_entropy_loss,iif_loss,fasa_iif_loss}.py`` are loaded by
+  path behind a stub ``mmcv`` (``jit`` -> identity decorator) and a stub registry
+  (``LOSSES.register_module()`` -> identity); no reference file is edited or copied.
+* The reference hard-codes ``device='cuda'`` (iif_loss.py:50) and ``torch.cuda.FloatTensor``
+  (custom.py:61); ``cpu_shims()`` remaps those two constructors to the CPU for the duration of a
+  ``with`` block so the unmodified code runs on a GPU-less host.
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib.util
+import os
+import sys
+import types
+
+REF = os.environ.get("IIF_REFERENCE_ROOT", "/root/reference")
+_LOSS_DIR = os.path.join(REF, "instance_segmentation", "mmdet", "models", "losses")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF, "classification", "custom.py"))
+
+
+def load_classification():
+    p = os.path.join(REF, "classification")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import custom  # noqa: the reference module
+    return custom
+
+
+def load_mmdet_losses():
+    """Returns a namespace with utils, accuracy, cross_entropy_loss, iif_loss, fasa_iif_loss."""
+    if "mmdet.models.losses.iif_loss" in sys.modules:
+        return types.SimpleNamespace(**{m: sys.modules["mmdet.models.losses." + m] for m in
+                                        ("utils", "accuracy", "cross_entropy_loss", "iif_loss", "fasa_iif_loss")})
+    mmcv = types.ModuleType("mmcv")
+    mmcv.jit = lambda *a, **k: (lambda f: f)
+    sys.modules.setdefault("mmcv", mmcv)
+    for n in ("mmdet", "mmdet.models", "mmdet.models.losses"):
+        if n not in sys.modules:
+            m = types.ModuleType(n)
+            m.__path__ = []
+            sys.modules[n] = m
+    b = types.ModuleType("mmdet.models.builder")
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda c: c
+
+    b.LOSSES = _Reg()
+    sys.modules["mmdet.models.builder"] = b
+    out = {}
+    for mod in ("utils", "accuracy", "cross_entropy_loss", "iif_loss", "fasa_iif_loss"):
+        if mod == "fasa_iif_loss":
+            pkg = sys.modules["mmdet.models.losses"]
+            pkg.binary_cross_entropy = out["cross_entropy_loss"].binary_cross_entropy
+            pkg.mask_cross_entropy = out["cross_entropy_loss"].mask_cross_entropy
+        spec = importlib.util.spec_from_file_location("mmdet.models.losses." + mod,
+                                                      os.path.join(_LOSS_DIR, mod + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = m
+        spec.loader.exec_module(m)
+        out[mod] = m
+    return types.SimpleNamespace(**out)
+
+
+@contextlib.contextmanager
+def cpu_shims():
+    """Run reference code that names CUDA on a CPU-only host (device remap only)."""
+    import torch
+
+    real_tensor, real_zeros = torch.tensor, torch.zeros
+    real_cuda_ft = getattr(torch.cuda, "FloatTensor", None)
+    real_t_cuda = torch.Tensor.cuda
+
+    def tensor(*a, **k):
+        if str(k.get("device", "")).startswith("cuda"):
+            k["device"] = "cpu"
+        return real_tensor(*a, **k)
+
+    torch.tensor = tensor
+    torch.cuda.FloatTensor = torch.FloatTensor
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.tensor = real_tensor
+        torch.zeros = real_zeros
+        torch.Tensor.cuda = real_t_cuda
+        if real_cuda_ft is not None:
+            torch.cuda.FloatTensor = real_cuda_ft
+
+
+def csv_path(name: str) -> str:
+    sub = "coco_files" if name == "idf_91.csv" else "lvis_files"
+    return os.path.join(REF, "instance_segmentation", sub, name)

@@ -1,0 +1,237 @@
+"""Freeze golden vectors by running the UNMODIFIED reference Python (build container only).
+
+    python tests/golden/make_golden.py          # needs /root/reference
+
+Writes ``tests/golden/*.npz``.  Inputs are seeded (torch.manual_seed / numpy default_rng) and
+stored next to the reference's outputs, so the fixtures are self-contained on the GPU box where
+/root/reference does not exist.  Reference entry points exercised:
+
+* ``classification/custom.py``: IIFLoss (all 7 variants, reductions, iif_norm, class weight,
+  infer=True), FocalLoss(gamma=0) (via the cpu shim for ``torch.cuda.FloatTensor``)
+* ``mmdet/models/losses/iif_loss.py``: IIFLoss.forward / get_activation / get_accuracy
+* ``mmdet/models/losses/fasa_iif_loss.py``: FasaIIFLoss softmax, sigmoid, use_cums
+* ``mmdet/models/losses/cross_entropy_loss.py``: CrossEntropyLoss(use_sigmoid=True)
+* ``lvis_files/idf_1204.csv``, ``idf_1231.csv``, ``coco_files/idf_91.csv`` weight tables
+"""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_loader  # noqa: E402
+
+assert ref_loader.available(), "reference tree not found"
+custom = ref_loader.load_classification()
+mm = ref_loader.load_mmdet_losses()
+
+VARIANTS = ["raw", "smooth", "rel", "normit", "gombit", "base2", "base10"]
+CSV_COLS = ["smooth", "raw", "prob", "normit", "gombit", "base2", "base10"]
+CSV_COLS = CSV_COLS + [c + "_obj" for c in CSV_COLS]
+
+
+class _DS:
+    def __init__(self, counts):
+        self.c = list(counts)
+
+    def get_cls_num_list(self):
+        return self.c
+
+
+def npy(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def lt_labels(counts, n, gen):
+    p = torch.tensor(counts, dtype=torch.float64)
+    return torch.multinomial(p / p.sum(), n, replacement=True, generator=gen)
+
+
+# ------------------------------------------------------------------ classification IIFLoss
+def gen_cls_iif():
+    g = torch.Generator().manual_seed(0)
+    counts = [5000, 2997, 1796, 1077, 645, 387, 232, 139, 83, 50]  # imbalanced_dataset.py:23-29, r=100
+    B, D, C = 128, 64, 10
+    x = torch.randn(B, D, generator=g)
+    w = (torch.rand(C, D, generator=g) * 2 - 1) / D ** 0.5
+    b = torch.full((C,), 0.01)
+    y = lt_labels(counts, B, g)
+    cw = torch.tensor(counts, dtype=torch.float32)
+    cw = cw.sum() / cw  # initialisers.get_weights (--deffered)
+    out = dict(counts=np.array(counts), x=npy(x), w=npy(w), b=npy(b), y=npy(y), cw=npy(cw))
+
+    def run(crit, tag, reduction):
+        xx = x.clone().requires_grad_(True)
+        ww = w.clone().requires_grad_(True)
+        bb = b.clone().requires_grad_(True)
+        z = torch.nn.functional.linear(xx, ww, bb)
+        z.retain_grad()
+        loss = crit(z, y)
+        (loss.sum() if reduction == "none" else loss).backward()
+        out[f"loss_{tag}"] = npy(loss)
+        out[f"dz_{tag}"] = npy(z.grad)
+        out[f"dx_{tag}"] = npy(xx.grad)
+        out[f"dw_{tag}"] = npy(ww.grad)
+        out[f"db_{tag}"] = npy(bb.grad)
+        out["z"] = npy(z)
+
+    for v in VARIANTS:
+        crit = custom.IIFLoss(_DS(counts), variant=v, device="cpu")
+        out[f"iif_{v}"] = npy(crit.iif[v])
+        run(crit, f"{v}_mean", "mean")
+        out[f"infer_{v}"] = npy(crit(torch.from_numpy(out["z"]), infer=True))
+        critn = custom.IIFLoss(_DS(counts), variant=v, iif_norm=2, device="cpu")
+        out[f"iifn2_{v}"] = npy(critn.iif[v])
+    for r in ("sum", "none"):
+        for v in ("raw", "smooth"):
+            run(custom.IIFLoss(_DS(counts), variant=v, reduction=r, device="cpu"), f"{v}_{r}", r)
+    run(custom.IIFLoss(_DS(counts), variant="smooth", device="cpu", weight=cw), "smooth_cw_mean", "mean")
+    run(custom.IIFLoss(_DS(counts), variant="raw", iif_norm=2, device="cpu"), "raw_n2_mean", "mean")
+    np.savez_compressed(os.path.join(HERE, "cls_iif.npz"), **out)
+
+
+# ------------------------------------------------------------------ classification BCE (FocalLoss gamma=0)
+def gen_cls_bce():
+    g = torch.Generator().manual_seed(1)
+    B, C = 64, 37
+    z0 = torch.randn(B, C, generator=g) * 3
+    y = torch.randint(0, C, (B,), generator=g)
+    wts = torch.rand(C, generator=g) + 0.5
+    out = dict(z=npy(z0), y=npy(y), weights=npy(wts))
+    with ref_loader.cpu_shims():
+        for red in ("mean", "sum"):
+            for tag, ww in (("now", None), ("w", wts)):
+                crit = custom.FocalLoss(gamma=0, reduction=red, device="cpu", weights=ww)
+                z = z0.clone().requires_grad_(True)
+                loss = crit(z, y)
+                loss.backward()
+                out[f"loss_{tag}_{red}"] = npy(loss)
+                out[f"dz_{tag}_{red}"] = npy(z.grad)
+    np.savez_compressed(os.path.join(HERE, "cls_bce.npz"), **out)
+
+
+# ------------------------------------------------------------------ mmdet IIFLoss / FasaIIFLoss
+def gen_mmdet():
+    g = torch.Generator().manual_seed(2)
+    path = ref_loader.csv_path("idf_1204.csv")
+    B, C = 32, 1204
+    z0 = torch.randn(B, C, generator=g) * 2
+    y = torch.randint(0, 1203, (B,), generator=g)
+    y[torch.rand(B, generator=g) < 0.6] = 1203  # background
+    y[5] = -100
+    y[17] = -100
+    wrow = (torch.rand(B, generator=g) > 0.15).float() * (0.5 + torch.rand(B, generator=g))
+    avg = max(float((wrow > 0).sum()), 1.0)  # bbox_head.py:267
+    cwl = (0.5 + torch.rand(C, generator=g)).tolist()
+    out = dict(z=npy(z0), y=npy(y), w=npy(wrow), avg_factor=np.float64(avg), class_weight=np.array(cwl, np.float64))
+
+    def run(crit, tag, yy=None, rows=None, **kw):
+        z = z0.clone().requires_grad_(True)
+        loss = crit(z, y if yy is None else yy, **kw)
+        loss.sum().backward()
+        out[f"loss_{tag}"] = npy(loss)
+        out[f"dz_{tag}"] = npy(z.grad)[:rows]  # the 14-column sweep keeps the first 8 rows only
+
+    with ref_loader.cpu_shims():
+        for col in CSV_COLS:
+            crit = mm.iif_loss.IIFLoss(path=path, variant=col, num_classes=1203)
+            out[f"iif_{col}"] = npy(crit.iif_weights)
+            run(crit, f"{col}_avg", rows=8, weight=wrow, avg_factor=avg)
+        crit = mm.iif_loss.IIFLoss(path=path, variant="raw", num_classes=1203)
+        run(crit, "raw_plain")
+        run(crit, "raw_w_mean", weight=wrow)
+        run(crit, "raw_none", weight=wrow, reduction_override="none")
+        run(crit, "raw_sum", weight=wrow, reduction_override="sum")
+        run(crit, "raw_none_avg", weight=wrow, avg_factor=avg, reduction_override="none")
+        run(crit, "raw_ignbg", yy=y.clamp(min=0), weight=wrow, avg_factor=avg, ignore_index=1203)
+        out["act_raw"] = npy(crit.get_activation(z0))
+        out["acc_raw"] = npy(crit.get_accuracy(z0, y)["acc_classes"])
+        acc15 = mm.accuracy.accuracy(z0, y.clamp(min=0), topk=(1, 5))
+        out["acc_top1"] = npy(acc15[0])
+        out["acc_top5"] = npy(acc15[1])
+        out["topk5_idx"] = npy(z0.topk(5, dim=1)[1])
+        crit = mm.iif_loss.IIFLoss(path=path, variant="smooth", num_classes=1203, class_weight=cwl, loss_weight=0.5)
+        run(crit, "smooth_cw_lw", weight=wrow, avg_factor=avg)
+        crit = mm.iif_loss.IIFLoss(path=path, variant="normit_obj", num_classes=1203, reduction="sum")
+        run(crit, "normit_obj_sum")
+        # FasaIIFLoss: softmax (IIF applied), sigmoid (no IIF), cums
+        crit = mm.fasa_iif_loss.FasaIIFLoss(path=path, variant="base10_obj", num_classes=1203)
+        run(crit, "fasa_base10_obj_avg", weight=wrow, avg_factor=avg)
+        out["fasa_act"] = npy(crit.get_activation(z0))
+        crit = mm.fasa_iif_loss.FasaIIFLoss(path=path, variant="base10_obj", num_classes=1203, use_sigmoid=True)
+        run(crit, "fasa_sigmoid_avg", weight=wrow, avg_factor=avg)
+        crit = mm.fasa_iif_loss.FasaIIFLoss(path=path, variant="raw", num_classes=1203, use_cums=True)
+        ypos = y.clamp(min=0)
+        l1 = crit(z0, ypos)
+        l2 = crit(z0 * 0.5, ypos)
+        out["fasa_cum_losses"] = npy(crit.cum_losses)
+        out["fasa_cum_labels"] = npy(crit.cum_labels)
+        out["fasa_cum_ret"] = np.array([float(l1), float(l2)])
+    np.savez_compressed(os.path.join(HERE, "mmdet_iif.npz"), **out)
+
+
+# ------------------------------------------------------------------ mmdet sigmoid BCE
+def gen_mmdet_bce():
+    g = torch.Generator().manual_seed(3)
+    B, C = 24, 1203
+    z0 = torch.randn(B, C, generator=g) * 2
+    y = torch.randint(0, C, (B,), generator=g)
+    y[torch.rand(B, generator=g) < 0.5] = C  # background: no positive column
+    y[3] = 255
+    y[9] = -100
+    wrow = (torch.rand(B, generator=g) > 0.2).float() * (0.5 + torch.rand(B, generator=g))
+    avg = max(float((wrow > 0).sum()), 1.0)
+    pw = (0.5 + torch.rand(C, generator=g)).tolist()
+    out = dict(z=npy(z0), y=npy(y), w=npy(wrow), avg_factor=np.float64(avg), pos_weight=np.array(pw, np.float64))
+
+    def run(crit, tag, **kw):
+        z = z0.clone().requires_grad_(True)
+        loss = crit(z, y, **kw)
+        loss.sum().backward()
+        out[f"loss_{tag}"] = npy(loss)
+        out[f"dz_{tag}"] = npy(z.grad)
+
+    CE = mm.cross_entropy_loss.CrossEntropyLoss
+    run(CE(use_sigmoid=True), "plain")
+    run(CE(use_sigmoid=True), "avg", weight=wrow, avg_factor=avg)
+    run(CE(use_sigmoid=True, ignore_index=255), "ign255_avg", weight=wrow, avg_factor=avg)
+    run(CE(use_sigmoid=True, class_weight=pw, loss_weight=2.0), "pw_lw_avg", weight=wrow, avg_factor=avg)
+    run(CE(use_sigmoid=True), "none", weight=wrow, reduction_override="none")
+    run(CE(use_sigmoid=True), "sum", weight=wrow, reduction_override="sum")
+    # softmax CrossEntropyLoss == IIF with all-ones scale
+    zc = z0[:, :40].contiguous()
+    yc = torch.randint(0, 40, (B,), generator=g)
+    z = zc.clone().requires_grad_(True)
+    loss = CE()(z, yc, weight=wrow, avg_factor=avg)
+    loss.backward()
+    out.update(ce_z=npy(zc), ce_y=npy(yc), ce_loss=npy(loss), ce_dz=npy(z.grad))
+    np.savez_compressed(os.path.join(HERE, "mmdet_bce.npz"), **out)
+
+
+# ------------------------------------------------------------------ CSV weight tables
+def gen_tables():
+    out = {}
+    for name, n_img in (("idf_1204.csv", 100170), ("idf_1231.csv", 57263), ("idf_91.csv", 118287)):
+        df = pd.read_csv(ref_loader.csv_path(name))
+        key = name.split(".")[0]
+        out[f"{key}_img_freq"] = df["img_freq"].values[1:].astype(np.int64)
+        out[f"{key}_instance_freq"] = df["instance_freq"].values[1:].astype(np.int64)
+        out[f"{key}_n_img"] = np.int64(n_img)
+        for col in CSV_COLS:
+            out[f"{key}_{col}"] = df[col].values.astype(np.float64)  # row 0 = placeholder kept
+    np.savez_compressed(os.path.join(HERE, "weight_tables.npz"), **out)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    gen_cls_iif()
+    gen_cls_bce()
+    gen_mmdet()
+    gen_mmdet_bce()
+    gen_tables()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
