@@ -1,0 +1,101 @@
+"""Drop-in for classification/custom.py: IIFLoss, FocalLoss(gamma=0) and the accuracy helper.
+
+Same constructor / forward signatures, attribute names (`.iif`, `.variant`, `.reduction`) and
+reductions as the reference; the arithmetic runs in the fused CUDA kernels (no torch ops on the
+logits).  Reference lines are cited per method.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import functional as F_
+from . import histogram, ops
+
+
+class IIFLoss(nn.Module):
+    """classification/custom.py:6-39.
+
+    `IIFLoss(dataset, variant='raw', iif_norm=0, reduction='mean', device='cuda', weight=None)`;
+    `dataset.get_cls_num_list()` supplies the class counts.  `.iif` is the dict of seven [1,C] fp32
+    weight rows (callers test `hasattr(criterion, 'iif')`, train.py:104)."""
+
+    def __init__(self, dataset, variant="raw", iif_norm=0, reduction="mean", device="cuda", weight=None):
+        super().__init__()
+        self.reduction = reduction
+        self.variant = variant
+        self.weight = weight  # per-class CE weight (nn.CrossEntropyLoss(weight=...), custom.py:10)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("iif_b200.IIFLoss needs a CUDA device: the weight vector, the loss and its "
+                               "gradient are computed by CUDA kernels and there is no CPU fallback")
+        counts = torch.as_tensor(list(dataset.get_cls_num_list()), dtype=torch.int64).to(dev)
+        self.iif = histogram.iif_weight_dict(counts, iif_norm=float(iif_norm) if iif_norm > 0 else 0.0)
+
+    def forward(self, pred, targets=None, infer=False):
+        s = self.iif[self.variant]
+        if infer is not False:  # custom.py:37-39: adjusted logits, no softmax
+            out, _, _ = ops.scaled_activation(pred.float(), s, softmax=False)
+            return out
+        B = pred.shape[0]
+        if self.reduction == "mean":  # plain mean even with class weights (custom.py:32-33)
+            return F_.iif_cross_entropy(pred, s, targets, class_weight=self.weight, scale=1.0 / max(B, 1))
+        if self.reduction == "sum":
+            return F_.iif_cross_entropy(pred, s, targets, class_weight=self.weight, scale=1.0)
+        return F_.iif_cross_entropy(pred, s, targets, class_weight=self.weight, scale=1.0, reduce=False)
+
+
+class FocalLoss(nn.Module):
+    """classification/custom.py:42-89, gamma == 0 branch (= sigmoid BCE, `--classif bce`).
+
+    The one-hot target tensor of the reference (:61-63) is never built.  gamma > 0 (the focal
+    branch, :74-89) is outside the IIF hot path and not provided."""
+
+    def __init__(self, gamma, alpha=None, reduction="mean", device="cuda", weights=None):
+        super().__init__()
+        if gamma != 0:
+            raise NotImplementedError("iif_b200.FocalLoss implements the gamma == 0 (sigmoid BCE) branch only")
+        self.gamma, self.alpha, self.reduction = gamma, alpha, reduction
+        self.weights = weights.unsqueeze(0) if weights is not None else 1
+
+    def set_weights(self, weights):
+        self.weights = weights.unsqueeze(0)
+
+    def forward(self, pred, targets):
+        B, C = pred.shape
+        colw = None if isinstance(self.weights, int) else self.weights.reshape(-1)
+        # 'sum' -> sum / B ; anything else -> mean over B*C (custom.py:67-70)
+        scale = 1.0 / max(B, 1) if self.reduction == "sum" else 1.0 / max(B * C, 1)
+        return F_.sigmoid_bce(pred, targets, col_weight=colw, scale=scale)
+
+
+class Mixup(object):
+    """classification/custom.py:91-117 (unchanged semantics; the criterion is called twice)."""
+
+    def __init__(self, criterion, alpha=1):
+        self.alpha = alpha
+        self.criterion = criterion
+
+    def __call__(self, x, y, use_cuda=True):
+        import numpy as np
+        lam = np.random.beta(self.alpha, self.alpha) if self.alpha > 0 else 1
+        index = torch.randperm(x.size()[0], device=x.device if use_cuda else "cpu")
+        mixed_x = lam * x + (1 - lam) * x[index, :]
+        return mixed_x, y, y[index], lam
+
+    def mixup_criterion(self, pred, y_a, y_b, lam):
+        return lam * self.criterion(pred, y_a) + (1 - lam) * self.criterion(pred, y_b)
+
+
+def accuracy(output, target, topk=(1,)):
+    """classification/utils.py:165-179: top-k hit rate x 100/B, one fused pass (rank of the label)."""
+    with torch.no_grad():
+        r = ops.softmax_ce(output.float(), None, target, want_dz_f32=False, want_acc=True, want_sum=False)
+        B = target.size(0)
+        return [(r["rank"] < k).sum(dtype=torch.float32) * (100.0 / B) for k in topk]
+
+
+def predictions(output, iif=None):
+    """argmax of the (optionally IIF-adjusted) logits, first index on ties (per_shot_acc.py:130)."""
+    _, am, _ = ops.scaled_activation(output.float(), iif, softmax=False, want_pred=True)
+    return am.long()

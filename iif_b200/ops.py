@@ -1,0 +1,393 @@
+"""Tensor-level wrappers over the C ABI: raw device pointers + the current CUDA stream.
+
+torch is plumbing here (device memory, streams); every arithmetic op of the path runs in the
+hand-written kernels of libiif_b200.so.  CPU tensors are rejected loudly -- there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_WS = {}      # (device index, stream, bytes) -> zeroed workspace
+_TICKET = {}  # (device index, stream) -> zeroed int32[1]
+
+
+def _cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"iif_b200: `{name}` must be a CUDA tensor (no CPU fallback exists); got "
+                           f"{getattr(t, 'device', type(t))}")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"iif_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _rows(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    """2-D, unit inner stride (any leading dimension)."""
+    _cuda(t, name, dtype)
+    if t.dim() != 2:
+        raise ValueError(f"iif_b200: `{name}` must be 2-D, got shape {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.shape[1]), 1)
+
+
+def _vec(t: Optional[torch.Tensor], name: str, n: int, dtype=torch.float32):
+    if t is None:
+        return None
+    _cuda(t, name)
+    t = t.reshape(-1)
+    if t.numel() != n:
+        raise ValueError(f"iif_b200: `{name}` must have {n} elements, got {t.numel()}")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ticket(device) -> torch.Tensor:
+    key = (torch.device(device).index or 0, torch.cuda.current_stream(device).cuda_stream)
+    t = _TICKET.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _TICKET[key] = t
+    return t
+
+
+def gemm_workspace(B: int, D: int, Cc: int, device) -> Optional[torch.Tensor]:
+    n = int(_lib.load().iif_gemm_ws_bytes(B, D, Cc))
+    if n == 0:
+        return None
+    key = (torch.device(device).index or 0, torch.cuda.current_stream(device).cuda_stream)
+    t = _WS.get(key)
+    if t is None or t.numel() < n:
+        t = torch.zeros(n, dtype=torch.uint8, device=device)  # zeroed once; kernels keep the tickets zero
+        _WS[key] = t
+    return t
+
+
+def launch_count() -> int:
+    return int(_lib.load().iif_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# histogram + weights
+# ------------------------------------------------------------------------------------------------
+def hist_labels(labels: torch.Tensor, num_classes: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    labels = _cuda(labels, "labels", torch.int64).reshape(-1).contiguous()
+    if out is None:
+        out = torch.zeros(num_classes, dtype=torch.int64, device=labels.device)
+    _lib.check(_lib.load().iif_hist_labels_i64(_ptr(labels), labels.numel(), _ptr(out), num_classes,
+                                               _stream(labels.device)), "hist_labels")
+    return out
+
+
+def hist_images_dedup(image_ids: torch.Tensor, categories: torch.Tensor, num_images: int, num_classes: int):
+    image_ids = _cuda(image_ids, "image_ids", torch.int64).reshape(-1).contiguous()
+    categories = _cuda(categories, "categories", torch.int64).reshape(-1).contiguous()
+    if image_ids.numel() != categories.numel():
+        raise ValueError("image_ids and categories must have the same length")
+    dev = image_ids.device
+    lib = _lib.load()
+    ws = torch.zeros(max(int(lib.iif_hist_images_dedup_ws_bytes(num_images, num_classes)) // 4, 1),
+                     dtype=torch.int32, device=dev)
+    img = torch.zeros(num_classes, dtype=torch.int64, device=dev)
+    inst = torch.zeros(num_classes, dtype=torch.int64, device=dev)
+    _lib.check(lib.iif_hist_images_dedup_i64(_ptr(image_ids), _ptr(categories), image_ids.numel(), num_images,
+                                             num_classes, _ptr(img), _ptr(inst), _ptr(ws), _stream(dev)),
+               "hist_images_dedup")
+    return img, inst
+
+
+def weights_from_counts(counts: torch.Tensor, variant: str, total: int = 0, norm_p: float = 0.0,
+                        return_f64: bool = False):
+    counts = _cuda(counts, "counts", torch.int64).reshape(-1).contiguous()
+    if variant not in _lib.VARIANT_IDS:
+        raise KeyError(variant)
+    n = counts.numel()
+    out = torch.empty(n, dtype=torch.float32, device=counts.device)
+    o64 = torch.empty(n, dtype=torch.float64, device=counts.device) if return_f64 else None
+    _lib.check(_lib.load().iif_weights_from_counts(_ptr(counts), n, int(total), _lib.VARIANT_IDS[variant],
+                                                   float(norm_p), _ptr(out), _ptr(o64), _stream(counts.device)),
+               "weights_from_counts")
+    return (out, o64) if return_f64 else out
+
+
+# ------------------------------------------------------------------------------------------------
+# loss kernels
+# ------------------------------------------------------------------------------------------------
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def softmax_ce(z, iif, label, *, class_weight=None, sample_weight=None, ignore_index=-100, scale=1.0,
+               want_dz_f32=True, want_dz_bf16=False, want_acc=False, want_sum=True, want_lse=False):
+    """Returns dict(loss_i, loss_sum, dz_f32, dz_bf16 [B,pad8(C)], argmax, rank, acc_counts, lse)."""
+    z = _rows(z, "z", torch.float32)
+    B, Cc = z.shape
+    dev = z.device
+    label = _vec(label, "label", B, torch.int64)
+    iif = _vec(iif, "iif", Cc)
+    cw = _vec(class_weight, "class_weight", Cc)
+    sw = _vec(sample_weight, "sample_weight", B)
+    r = dict(loss_i=torch.empty(B, dtype=torch.float32, device=dev))
+    r["loss_sum"] = torch.zeros((), dtype=torch.float32, device=dev) if want_sum else None
+    r["dz_f32"] = torch.empty(B, Cc, dtype=torch.float32, device=dev) if want_dz_f32 else None
+    r["dz_bf16"] = torch.empty(B, pad8(Cc), dtype=torch.bfloat16, device=dev) if want_dz_bf16 else None
+    r["argmax"] = torch.empty(B, dtype=torch.int32, device=dev) if want_acc else None
+    r["rank"] = torch.empty(B, dtype=torch.int32, device=dev) if want_acc else None
+    r["acc_counts"] = torch.zeros(2, dtype=torch.int32, device=dev) if want_acc else None
+    r["lse"] = torch.empty(B, dtype=torch.float32, device=dev) if want_lse else None
+    if B == 0:
+        return r
+    tk = ticket(dev)
+    _lib.check(_lib.load().iif_softmax_ce_fwd_bwd(
+        _ptr(z), _ld(z), _ptr(iif), _ptr(label), _ptr(cw), _ptr(sw), int(ignore_index), float(scale), B, Cc,
+        _ptr(r["loss_i"]), _ptr(r["loss_sum"]), _ptr(r["dz_f32"]), Cc, _ptr(r["dz_bf16"]), pad8(Cc), _ptr(r["lse"]),
+        _ptr(r["argmax"]), _ptr(r["rank"]), _ptr(r["acc_counts"]), _ptr(tk), _stream(dev)), "softmax_ce_fwd_bwd")
+    return r
+
+
+def scaled_activation(z, iif, softmax: bool, label=None, want_pred=False):
+    z = _rows(z, "z", torch.float32)
+    B, Cc = z.shape
+    dev = z.device
+    iif = _vec(iif, "iif", Cc)
+    out = torch.empty(B, Cc, dtype=torch.float32, device=dev)
+    lab = _vec(label, "label", B, torch.int64) if label is not None else None
+    am = torch.empty(B, dtype=torch.int32, device=dev) if want_pred else None
+    rk = torch.empty(B, dtype=torch.int32, device=dev) if (want_pred and lab is not None) else None
+    if B:
+        _lib.check(_lib.load().iif_scaled_activation(_ptr(z), _ld(z), _ptr(iif), int(bool(softmax)), B, Cc, _ptr(out),
+                                                     Cc, _ptr(lab), _ptr(am), _ptr(rk), _stream(dev)),
+                   "scaled_activation")
+    return out, am, rk
+
+
+def sigmoid_bce(z, label, *, pos_weight=None, col_weight=None, sample_weight=None, ignore_index=-100, scale=1.0,
+                want_elem=False, want_dz_f32=True, want_dz_bf16=False, want_sum=True):
+    z = _rows(z, "z", torch.float32)
+    B, Cc = z.shape
+    dev = z.device
+    label = _vec(label, "label", B, torch.int64)
+    pw = _vec(pos_weight, "pos_weight", Cc)
+    colw = _vec(col_weight, "col_weight", Cc)
+    sw = _vec(sample_weight, "sample_weight", B)
+    r = dict(loss_i=torch.empty(B, dtype=torch.float32, device=dev))
+    r["loss_sum"] = torch.zeros((), dtype=torch.float32, device=dev) if want_sum else None
+    r["loss_elem"] = torch.empty(B, Cc, dtype=torch.float32, device=dev) if want_elem else None
+    r["dz_f32"] = torch.empty(B, Cc, dtype=torch.float32, device=dev) if want_dz_f32 else None
+    r["dz_bf16"] = torch.empty(B, pad8(Cc), dtype=torch.bfloat16, device=dev) if want_dz_bf16 else None
+    if B == 0:
+        return r
+    _lib.check(_lib.load().iif_sigmoid_bce_fwd_bwd(
+        _ptr(z), _ld(z), _ptr(label), _ptr(pw), _ptr(colw), _ptr(sw), int(ignore_index), float(scale), B, Cc,
+        _ptr(r["loss_elem"]), Cc, _ptr(r["loss_i"]), _ptr(r["loss_sum"]), _ptr(r["dz_f32"]), Cc, _ptr(r["dz_bf16"]),
+        pad8(Cc), _ptr(ticket(dev)), _stream(dev)), "sigmoid_bce_fwd_bwd")
+    return r
+
+
+def scale_rows(x, g=None, *, bf16=False, pad_ld=False):
+    """x[rows, cols] fp32 * g (None | 0-dim device scalar | [rows]) -> fp32 or bf16 (optionally ld padded to 8)."""
+    x = _rows(x, "x", torch.float32)
+    rows, cols = x.shape
+    dev = x.device
+    gs = 0
+    if g is not None:
+        g = _cuda(g, "g")
+        g = g.to(torch.float32).reshape(-1).contiguous()
+        if g.numel() not in (1, rows):
+            raise ValueError("g must be a scalar or have one entry per row")
+        gs = 0 if g.numel() == 1 and rows != 1 else (1 if g.numel() == rows and rows > 1 else 0)
+    ldo = pad8(cols) if (bf16 and pad_ld) else cols
+    out = torch.empty(rows, ldo, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
+    if rows and cols:
+        _lib.check(_lib.load().iif_scale_rows(_ptr(x), _ld(x), _ptr(g), gs, rows, cols, _ptr(out),
+                                              _lib.DTYPE_BF16 if bf16 else _lib.DTYPE_F32, ldo, _stream(dev)),
+                   "scale_rows")
+    return out if ldo == cols else out[:, :cols]
+
+
+def colsum(dz, alpha=None):
+    _cuda(dz, "dz")
+    rows, cols = dz.shape
+    dt = _lib.DTYPE_BF16 if dz.dtype == torch.bfloat16 else _lib.DTYPE_F32
+    if dz.dtype not in (torch.bfloat16, torch.float32) or (cols > 1 and dz.stride(1) != 1):
+        raise TypeError("colsum expects fp32/bf16 rows with unit inner stride")
+    db = torch.empty(cols, dtype=torch.float32, device=dz.device)
+    al = None if alpha is None else _cuda(alpha, "alpha").to(torch.float32).reshape(-1)[:1].contiguous()
+    _lib.check(_lib.load().iif_colsum(_ptr(dz), dt, _ld(dz), _ptr(al), rows, cols, _ptr(db), _stream(dz.device)),
+               "colsum")
+    return db
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMMs
+# ------------------------------------------------------------------------------------------------
+def _alpha(alpha, dev):
+    if alpha is None:
+        return None
+    return _cuda(alpha, "alpha").to(torch.float32).reshape(-1)[:1].contiguous()
+
+
+def _bf16_rows(t, name):
+    t = _rows(t, name, torch.bfloat16)
+    if _ld(t) % 8 or t.data_ptr() % 16:
+        c = t.shape[1]
+        buf = torch.empty(t.shape[0], pad8(c), dtype=torch.bfloat16, device=t.device)
+        buf[:, :c].copy_(t)
+        t = buf[:, :c]
+    return t
+
+
+def linear_fwd(x, w, bias=None, col_scale=None, *, want_raw=True, want_scaled=False):
+    """Z = X W^T + b (and optionally Z * col_scale).  dtype of x/w selects the kernel: bf16 -> tcgen05, fp32 -> FFMA."""
+    bf = x.dtype == torch.bfloat16
+    if w.dtype != x.dtype:
+        raise TypeError(f"x ({x.dtype}) and w ({w.dtype}) must share a dtype")
+    x = _bf16_rows(x, "x") if bf else _rows(x, "x", torch.float32)
+    w = _bf16_rows(w, "w") if bf else _rows(w, "w", torch.float32)
+    B, D = x.shape
+    Cc, D2 = w.shape
+    if D != D2:
+        raise ValueError(f"shape mismatch: x {tuple(x.shape)} vs w {tuple(w.shape)}")
+    dev = x.device
+    bias = _vec(bias, "bias", Cc)
+    cs = _vec(col_scale, "col_scale", Cc)
+    z = torch.empty(B, Cc, dtype=torch.float32, device=dev) if want_raw else None
+    zs = torch.empty(B, Cc, dtype=torch.float32, device=dev) if (want_scaled and cs is not None) else None
+    if B == 0:
+        return z, zs
+    lib = _lib.load()
+    if bf:
+        ws = gemm_workspace(B, D, Cc, dev)
+        _lib.check(lib.iif_linear_fwd_bf16(_ptr(x), _ld(x), _ptr(w), _ld(w), _ptr(bias), _ptr(cs), _ptr(z), Cc,
+                                           _ptr(zs), Cc, B, D, Cc, _ptr(ws), 0 if ws is None else ws.numel(),
+                                           _stream(dev)), "linear_fwd_bf16")
+    else:
+        _lib.check(lib.iif_linear_fwd_f32(_ptr(x), _ld(x), _ptr(w), _ld(w), _ptr(bias), _ptr(cs), _ptr(z), Cc,
+                                          _ptr(zs), Cc, B, D, Cc, _stream(dev)), "linear_fwd_f32")
+    return z, zs
+
+
+def linear_bwd_dx(dz, w, alpha=None, out_bf16=False):
+    bf = dz.dtype == torch.bfloat16
+    dz = _bf16_rows(dz, "dz") if bf else _rows(dz, "dz", torch.float32)
+    w = _bf16_rows(w, "w") if bf else _rows(w, "w", torch.float32)
+    B, Cc = dz.shape
+    D = w.shape[1]
+    dev = dz.device
+    al = _alpha(alpha, dev)
+    lib = _lib.load()
+    if bf:
+        dx = torch.empty(B, D, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        if B:
+            ws = gemm_workspace(B, D, Cc, dev)
+            _lib.check(lib.iif_linear_bwd_dx_bf16(_ptr(dz), _ld(dz), _ptr(w), _ld(w), _ptr(al), _ptr(dx),
+                                                  _lib.DTYPE_BF16 if out_bf16 else _lib.DTYPE_F32, D, B, D, Cc,
+                                                  _ptr(ws), 0 if ws is None else ws.numel(), _stream(dev)),
+                       "linear_bwd_dx_bf16")
+    else:
+        dx = torch.empty(B, D, dtype=torch.float32, device=dev)
+        if B:
+            _lib.check(lib.iif_linear_bwd_dx_f32(_ptr(dz), _ld(dz), _ptr(w), _ld(w), _ptr(al), _ptr(dx), D, B, D, Cc,
+                                                 _stream(dev)), "linear_bwd_dx_f32")
+    return dx
+
+
+def linear_bwd_dw(dz, x, alpha=None):
+    bf = dz.dtype == torch.bfloat16
+    dz = _bf16_rows(dz, "dz") if bf else _rows(dz, "dz", torch.float32)
+    x = _bf16_rows(x, "x") if bf else _rows(x, "x", torch.float32)
+    B, Cc = dz.shape
+    D = x.shape[1]
+    dev = dz.device
+    al = _alpha(alpha, dev)
+    dw = torch.empty(Cc, D, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    if bf:
+        ws = gemm_workspace(B, D, Cc, dev)
+        _lib.check(lib.iif_linear_bwd_dw_bf16(_ptr(dz), _ld(dz), _ptr(x), _ld(x), _ptr(al), _ptr(dw), D, B, D, Cc,
+                                              _ptr(ws), 0 if ws is None else ws.numel(), _stream(dev)),
+                   "linear_bwd_dw_bf16")
+    else:
+        _lib.check(lib.iif_linear_bwd_dw_f32(_ptr(dz), _ld(dz), _ptr(x), _ld(x), _ptr(al), _ptr(dw), D, B, D, Cc,
+                                             _stream(dev)), "linear_bwd_dw_f32")
+    return dw
+
+
+class HeadStep:
+    """Pre-allocated buffers + one C call (`iif_head_fwd_bwd_bf16`) per head step.
+
+    fc_cls -> IIF softmax-CE fwd+bwd -> db, dX, dW with bf16 GEMM operands.  Buffers are allocated
+    once so the step can be captured in a CUDA graph."""
+
+    def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False):
+        dev = torch.device(device)
+        self.B, self.D, self.C, self.device = B, D, Cc, dev
+        f32, i32 = torch.float32, torch.int32
+        self.z = torch.empty(B, Cc, dtype=f32, device=dev)
+        self.loss_i = torch.empty(B, dtype=f32, device=dev)
+        self.loss = torch.zeros((), dtype=f32, device=dev)
+        self.dz = torch.empty(B, pad8(Cc), dtype=torch.bfloat16, device=dev)
+        self.dx = torch.empty(B, D, dtype=torch.bfloat16 if dx_bf16 else f32, device=dev) if need_dx else None
+        self.dw = torch.empty(Cc, D, dtype=f32, device=dev)
+        self.db = torch.empty(Cc, dtype=f32, device=dev) if need_db else None
+        self.argmax = torch.empty(B, dtype=i32, device=dev) if want_acc else None
+        self.rank = torch.empty(B, dtype=i32, device=dev) if want_acc else None
+        self.acc_counts = torch.zeros(2, dtype=i32, device=dev) if want_acc else None
+        self.ticket = torch.zeros(1, dtype=i32, device=dev)
+        n = int(_lib.load().iif_gemm_ws_bytes(B, D, Cc))
+        self.ws = torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
+        self.ws_bytes = n
+        self.dx_dtype = _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32
+        self.launches_per_step = 3 + (1 if need_dx else 0) + (1 if need_db else 0)
+
+    def run(self, x, w, bias, iif, label, *, class_weight=None, sample_weight=None, ignore_index=-100,
+            scale=None):
+        B, D, Cc = self.B, self.D, self.C
+        _cuda(x, "x", torch.bfloat16)
+        _cuda(w, "w", torch.bfloat16)
+        _cuda(label, "label", torch.int64)
+        if tuple(x.shape) != (B, D) or tuple(w.shape) != (Cc, D) or label.numel() != B:
+            raise ValueError("HeadStep: shape mismatch")
+        if x.stride(1) != 1 or w.stride(1) != 1:
+            raise ValueError("HeadStep: x and w need unit inner stride")
+        a = _lib.HeadArgs()
+        a.x, a.ldx, a.w, a.ldw = x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0)
+        a.bias = None if bias is None else bias.data_ptr()
+        a.iif = None if iif is None else iif.data_ptr()
+        a.label = label.data_ptr()
+        a.class_weight = None if class_weight is None else class_weight.data_ptr()
+        a.sample_weight = None if sample_weight is None else sample_weight.data_ptr()
+        a.ignore_index = int(ignore_index)
+        a.scale = float(1.0 / B if scale is None else scale)
+        a.B, a.D, a.C = B, D, Cc
+        a.z, a.ldz = self.z.data_ptr(), Cc
+        a.loss_i, a.loss_sum = self.loss_i.data_ptr(), self.loss.data_ptr()
+        a.dz_bf16, a.lddz = self.dz.data_ptr(), self.dz.stride(0)
+        a.dx = None if self.dx is None else self.dx.data_ptr()
+        a.dx_dtype, a.lddx = self.dx_dtype, D
+        a.dw, a.lddw = self.dw.data_ptr(), D
+        a.db = None if self.db is None else self.db.data_ptr()
+        a.argmax = None if self.argmax is None else self.argmax.data_ptr()
+        a.rank = None if self.rank is None else self.rank.data_ptr()
+        a.acc_counts = None if self.acc_counts is None else self.acc_counts.data_ptr()
+        a.ticket = self.ticket.data_ptr()
+        a.ws, a.ws_bytes = self.ws.data_ptr(), self.ws_bytes
+        _lib.check(_lib.load().iif_head_fwd_bwd_bf16(C.byref(a), _stream(self.device)), "head_fwd_bwd_bf16")
+        return self.loss

@@ -1,0 +1,233 @@
+/* iif_b200.h -- C ABI of the B200-native IIF classifier head.
+ *
+ * Drop-in boundary for the one hot path of kostas1515/iif: fc_cls GEMM -> per-class IIF logit
+ * scale -> softmax-CE / sigmoid-BCE (forward + backward) and the label histogram that produces
+ * the IIF weight vector.  The reference has no FFI (it is pure Python on torch); every entry point
+ * below replaces the implicit ATen / cuBLAS dispatch made at the cited reference line
+ * (paths relative to the reference root; cls/ = classification/, seg/ = instance_segmentation/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller allocates every output
+ *   - all matrices are row-major with an explicit leading dimension (elements, not bytes)
+ *   - calls are stateless, stream-ordered and re-entrant across streams / ranks
+ *   - return value: 0 = ok, <0 = argument error (IIF_E*), >0 = cudaError_t of the launch
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*
+ *   - bf16 tensors are passed as void* (uint16 storage, torch.bfloat16 compatible)
+ */
+#ifndef IIF_B200_H_
+#define IIF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IIF_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define IIF_API __attribute__((visibility("default")))
+#else
+#define IIF_API
+#endif
+
+enum {
+  IIF_OK = 0,
+  IIF_EINVAL = -1,       /* null pointer / negative size / bad enum */
+  IIF_EALIGN = -2,       /* pointer or leading dimension violates the documented alignment */
+  IIF_EUNSUPPORTED = -3, /* shape outside the supported range (e.g. C > 32768 for the row kernels) */
+  IIF_EWORKSPACE = -4,   /* workspace too small */
+  IIF_EDRIVER = -5       /* cuTensorMapEncodeTiled unavailable / failed */
+};
+
+/* IIF weighting variants, cls/custom.py:16-23 (CSV column names in seg/lvis_files/idf_1204.csv:1
+ * use "prob" for REL). */
+enum {
+  IIF_VARIANT_RAW = 0,    /* ln(N/f)                 */
+  IIF_VARIANT_SMOOTH = 1, /* ln((N+1)/(f+1)) + 1     */
+  IIF_VARIANT_REL = 2,    /* ln((N-f)/f)             */
+  IIF_VARIANT_NORMIT = 3, /* -ndtri(f/N)             */
+  IIF_VARIANT_GOMBIT = 4, /* -ln(-ln(1 - f/N))       */
+  IIF_VARIANT_BASE2 = 5,  /* log2(N/f)               */
+  IIF_VARIANT_BASE10 = 6  /* log10(N/f)              */
+};
+
+enum { IIF_DTYPE_F32 = 0, IIF_DTYPE_BF16 = 1 };
+
+IIF_API int iif_abi_version(void);
+IIF_API const char* iif_error_string(int code);
+/* Number of kernels this library has launched since load (all streams); bench.py's gpu_launches. */
+IIF_API uint64_t iif_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (d) histograms + IIF weight vector
+ * ------------------------------------------------------------------------------------------- */
+
+/* counts[c] += #{i : labels[i] == c}, c in [0,C); labels outside [0,C) are ignored.
+ * Replaces the O(N*C) numpy loops cls/imbalanced_dataset.py:112,127.  `counts` is accumulated
+ * into (zero it first); integer, bit-exact. */
+IIF_API int iif_hist_labels_i64(const int64_t* labels, int64_t n, int64_t* counts, int64_t num_classes,
+                        void* stream);
+
+/* Per-annotation (image_id, category) pairs -> instance_freq[c] (#annotations) and img_freq[c]
+ * (#distinct images holding c): the two frequency columns of seg/lvis_files/idf_1204.csv (cols
+ * 15-16; set-dedup semantics of seg/mmdet/datasets/dataset_wrappers.py:245-252).
+ * `bitmap_ws`: num_classes * ceil(num_images/32) uint32 words, ZEROED by the caller; both outputs
+ * are accumulated into.  Pairs with category outside [0,C) or image outside [0,num_images) are
+ * ignored. */
+IIF_API int iif_hist_images_dedup_i64(const int64_t* image_ids, const int64_t* categories, int64_t n,
+                              int64_t num_images, int64_t num_classes, int64_t* img_freq,
+                              int64_t* instance_freq, uint32_t* bitmap_ws, void* stream);
+IIF_API size_t iif_hist_images_dedup_ws_bytes(int64_t num_images, int64_t num_classes);
+
+/* counts[C] -> weight vector, float64 arithmetic rounded ONCE to float32 (cls/custom.py:14-26;
+ * closed forms of the CSV columns read at seg/mmdet/models/losses/iif_loss.py:47-50).
+ *   total   : N; <= 0 means sum(counts) (classification).  The CSVs use #images / sum(instance_freq).
+ *   norm_p  : > 0 divides by the p-norm of the fp32 vector (iif_norm, cls/custom.py:25-26)
+ *   out_f32 : [C] required;  out_f64 : [C] optional un-normalised float64 values (may be NULL) */
+IIF_API int iif_weights_from_counts(const int64_t* counts, int64_t num_classes, int64_t total, int variant,
+                            double norm_p, float* out_f32, double* out_f64, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (b) fused softmax cross-entropy forward + backward with the IIF logit scale
+ * ------------------------------------------------------------------------------------------- */
+
+/* One pass over the logits.  With a = z * iif (per column), p = softmax(a):
+ *   l_i      = -cw[y_i] * w_i * log p_{i,y_i}          (0 when y_i == ignore_index or y_i outside [0,C))
+ *   loss_i   = scale * l_i                              [B]   optional
+ *   loss_sum = sum_i loss_i  (fixed-order, deterministic) [1] optional
+ *   dz_ic    = iif_c * scale * cw[y_i] * w_i * (p_ic - [c == y_i])       optional, fp32 and/or bf16
+ *   argmax_i = first index of max_c z_ic (RAW logits), rank_i = #{c: z_ic > z_iy} + #{c<y: z_ic == z_iy}
+ * Replaces `pred*iif` + F.cross_entropy + weight_reduce_loss + their autograd:
+ * cls/custom.py:28-36; seg/mmdet/models/losses/iif_loss.py:187-200, losses/utils.py:42-55.
+ * scale = 1/B (cls 'mean'), 1 ('sum'/'none'), loss_weight/avg_factor or loss_weight/B (mmdet).
+ * acc_counts[0..1] (optional) = #{rank_i < 1}, #{rank_i < 5} (cls/utils.py:165-179).
+ * `ticket`: one int32 device word, zero on entry, left zero on exit (inter-CTA ordering).
+ * Alignment: z and dz rows may use any leading dimension; 128-bit access is used when the base
+ * pointers are 16-byte aligned and ldz / lddz / C are multiples of 4 (8 for bf16 dz).
+ * Supported C: 1..32768. */
+IIF_API int iif_softmax_ce_fwd_bwd(const float* z, int64_t ldz, const float* iif, const int64_t* label,
+                           const float* class_weight, const float* sample_weight,
+                           int64_t ignore_index, float scale, int64_t B, int64_t C, float* loss_i,
+                           float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
+                           int64_t lddz_bf16, float* lse, int32_t* argmax, int32_t* rank,
+                           int32_t* acc_counts, int32_t* ticket, void* stream);
+
+/* out = softmax(z * iif) per row (seg/mmdet/models/losses/iif_loss.py:76) or, with
+ * softmax == 0, out = z * iif (cls/custom.py:38, infer=True).  argmax/rank (optional) are taken
+ * on the ADJUSTED logits here (cls/train.py:104-106). */
+IIF_API int iif_scaled_activation(const float* z, int64_t ldz, const float* iif, int softmax, int64_t B,
+                          int64_t C, float* out, int64_t ldo, const int64_t* label, int32_t* argmax,
+                          int32_t* rank, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (b') sigmoid BCE forward + backward (no IIF scale; no one-hot tensor is materialised)
+ * ------------------------------------------------------------------------------------------- */
+
+/* t_ic = [c == y_i] for 0 <= y_i < C and y_i != ignore_index; valid_i = (y_i >= 0 && y_i != ignore_index)
+ *   e_ic   = (1 - t) z + (1 + (pw_c - 1) t) * softplus(-z)                  (pw = pos_weight, optional)
+ *   wgt_ic = valid_i * w_i * colw_c                                          (w, colw optional)
+ *   loss_elem = scale * wgt * e [B,C] optional;  loss_i = row sums [B] optional;  loss_sum [1] optional
+ *   dz = scale * wgt * ((1 - t) - (1 + (pw - 1) t) (1 - sigmoid(z)))
+ * Replaces _expand_onehot_labels + F.binary_cross_entropy_with_logits + weight_reduce_loss:
+ * seg/mmdet/models/losses/cross_entropy_loss.py:53-111 (used by CrossEntropyLoss(use_sigmoid) and
+ * FasaIIFLoss(use_sigmoid), fasa_iif_loss.py:35-36) and cls FocalLoss(gamma=0), cls/custom.py:61-73
+ * (colw = per-class weights; scale = 1/(B*C) for 'mean', 1/B for 'sum'). */
+IIF_API int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_t* label,
+                            const float* pos_weight, const float* col_weight,
+                            const float* sample_weight, int64_t ignore_index, float scale,
+                            int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
+                            float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
+                            int64_t lddz_bf16, int32_t* ticket, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * small elementwise helpers on [rows, cols] matrices
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[i,c] = in[i,c] * g[i * g_stride]  (g == NULL -> 1).  g_stride 0 = one device scalar (the
+ * upstream autograd grad of a reduced loss), 1 = per-row vector (reduction='none').  Also the
+ * fp32 -> bf16 operand cast (out_dtype = IIF_DTYPE_BF16). */
+IIF_API int iif_scale_rows(const float* in, int64_t ldi, const float* g, int64_t g_stride, int64_t rows,
+                   int64_t cols, void* out, int out_dtype, int64_t ldo, void* stream);
+
+/* db[c] = alpha * sum_i dz[i,c]   (alpha_dev == NULL -> 1; fixed-order, deterministic).
+ * The bias gradient of AddmmBackward (a10). */
+IIF_API int iif_colsum(const void* dz, int dz_dtype, int64_t lddz, const float* alpha_dev, int64_t rows,
+               int64_t cols, float* db, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a)/(c) fc_cls GEMMs.  *_bf16: tcgen05.mma (TMEM accumulators, TMA-fed), bf16 operands, fp32
+ * accumulation.  *_f32: FFMA, fp32 operands (the 1e-5 parity mode).
+ * `ws`: workspace of at least iif_gemm_ws_bytes(...) bytes, ZEROED once by the caller (the kernels
+ * leave its ticket area zeroed); may be NULL when iif_gemm_ws_bytes returns 0.
+ * bf16 alignment: base pointers 16 bytes; leading dimensions of bf16 operands multiples of 8.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Z[B,C] = X[B,D] W[C,D]^T + bias (nn.Linear / fc_cls forward: cls/resnet_pytorch.py:219,293;
+ * cls/resnet_cifar.py:192,211; seg/.../bbox_heads/bbox_head.py:118, convfc_bbox_head.py:188).
+ * Epilogue: + bias[c] (optional); z (raw, optional) and zs = z * col_scale[c] (optional, the IIF
+ * adjusted logits of cls/custom.py:38) are written from the same accumulator. */
+IIF_API int iif_linear_fwd_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
+                        const float* col_scale, float* z, int64_t ldz, float* zs, int64_t ldzs,
+                        int64_t B, int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream);
+IIF_API int iif_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                       const float* col_scale, float* z, int64_t ldz, float* zs, int64_t ldzs,
+                       int64_t B, int64_t D, int64_t C, void* stream);
+
+/* dX[B,D] = alpha * dZ[B,C] W[C,D]   (AddmmBackward, a10).  alpha_dev: device scalar or NULL. */
+IIF_API int iif_linear_bwd_dx_bf16(const void* dz, int64_t lddz, const void* w, int64_t ldw,
+                           const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, int64_t B,
+                           int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream);
+IIF_API int iif_linear_bwd_dx_f32(const float* dz, int64_t lddz, const float* w, int64_t ldw,
+                          const float* alpha_dev, float* dx, int64_t lddx, int64_t B, int64_t D,
+                          int64_t C, void* stream);
+
+/* dW[C,D] = alpha * dZ[B,C]^T X[B,D]   (AddmmBackward, a10). */
+IIF_API int iif_linear_bwd_dw_bf16(const void* dz, int64_t lddz, const void* x, int64_t ldx,
+                           const float* alpha_dev, float* dw, int64_t lddw, int64_t B, int64_t D,
+                           int64_t C, void* ws, size_t ws_bytes, void* stream);
+IIF_API int iif_linear_bwd_dw_f32(const float* dz, int64_t lddz, const float* x, int64_t ldx,
+                          const float* alpha_dev, float* dw, int64_t lddw, int64_t B, int64_t D,
+                          int64_t C, void* stream);
+
+/* Workspace (bytes) the three bf16 GEMMs of a head of this shape may need (max over the three). */
+IIF_API size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C);
+
+/* ---------------------------------------------------------------------------------------------
+ * whole head, one call: fc_cls -> IIF softmax-CE fwd+bwd -> dX, dW, db   (bf16 GEMM mode)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct iif_head_args {
+  /* inputs */
+  const void* x;  int64_t ldx;        /* bf16 [B,D] */
+  const void* w;  int64_t ldw;        /* bf16 [C,D] */
+  const float* bias;                  /* [C] or NULL */
+  const float* iif;                   /* [C] or NULL (plain CE) */
+  const int64_t* label;               /* [B] */
+  const float* class_weight;          /* [C] or NULL */
+  const float* sample_weight;         /* [B] or NULL */
+  int64_t ignore_index;
+  float scale;                        /* see iif_softmax_ce_fwd_bwd */
+  int64_t B, D, C;
+  /* outputs (any may be NULL to skip, except z and dz_bf16 which the chain needs) */
+  float* z;       int64_t ldz;        /* raw logits fp32 [B,C] */
+  float* loss_i;                      /* [B] */
+  float* loss_sum;                    /* [1] */
+  void* dz_bf16;  int64_t lddz;       /* bf16 [B,lddz], lddz % 8 == 0 */
+  void* dx;       int dx_dtype; int64_t lddx;   /* [B,D]; NULL = frozen backbone (--decoup / selectp=1) */
+  float* dw;      int64_t lddw;       /* fp32 [C,D] */
+  float* db;                          /* fp32 [C] or NULL */
+  int32_t* argmax; int32_t* rank; int32_t* acc_counts;
+  /* scratch */
+  int32_t* ticket;                    /* 1 zeroed int32 */
+  void* ws; size_t ws_bytes;          /* iif_gemm_ws_bytes(B,D,C), zeroed once */
+} iif_head_args;
+
+/* Launches the 4-5 kernels of one head step on `stream` (cls/train.py:66-77 collapsed to the head;
+ * seg/.../bbox_head.py:118 + :269-274 + autograd). */
+IIF_API int iif_head_fwd_bwd_bf16(const iif_head_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IIF_B200_H_ */
