@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""IIF head fwd+bwd throughput (samples/s) on B200 -- the metric of BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape B,D,C]
+
+One "step" = one pass of the hot path over one batch of synthetic features/labels:
+fc_cls GEMM -> IIF softmax-CE fwd+bwd -> db, dX, dW (bf16 GEMM operands, fp32 accumulate), through
+the C ABI (`iif_head_fwd_bwd_bf16`).  At N > 1 every rank processes its own B rows (weak scaling,
+row sharding) and the head's parameter gradients (dW, db: one flat fp32 buffer) are all-reduced
+(mean) over NCCL on a side stream, overlapping the next step's compute.
+
+Timing hygiene: the step rotates through S independent sets of inputs AND outputs whose combined
+footprint exceeds the 126 MB L2, so no step finds its operands in L2 (config.l2 says so); CUDA
+events on the launching stream, barrier + synchronize on both sides, max over ranks.
+
+`--impl reference` times the CPU arm: the fp32 torch restatement of the reference step
+(oracle/torch_port.py -- the reference's own Python cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "IIF head fwd+bwd samples/s"
+UNIT = "samples/s"
+WORKLOAD = "ImageNet-LT ResNet-50 IIF head (2048-d x 1000 classes, batch 256/GPU, bf16 GEMM) fwd+bwd"
+L2_BYTES = 126e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="256,2048,1000", help="B(per GPU),D,C")
+    ap.add_argument("--variant", default="smooth")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--sync-allreduce", action="store_true", help="N>1: all-reduce on the compute stream (no overlap)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")  # B200_PROFILING.md fallback
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML polling thread)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(B, D, C, seconds, steps=None, warmup=3):
+    """The reference step restated in fp32 torch on the host cores (oracle/torch_port.py)."""
+    from oracle import torch_port as tp
+    cores = len(os.sched_getaffinity(0))
+    probe = tp.time_head_step(B, D, C, steps=2, warmup=1, threads=cores)
+    n = steps if steps is not None else max(5, min(int(seconds / max(probe, 1e-6)), 5000))
+    t = tp.time_head_step(B, D, C, steps=n, warmup=warmup, threads=cores)
+    return dict(value=B / t, unit=UNIT, cores=cores, kind="port", ms_per_step=t * 1e3,
+                sample=f"{n} steps of the same {B}x{D}x{C} fp32 head step (F.linear -> z*iif -> "
+                       f"F.cross_entropy -> backward) on {cores} torch threads, oracle/torch_port.py")
+
+
+def run_reference(args, B, D, C):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # each "step" is one CPU head step; bound the whole run to a few minutes
+    steps = max(1, min(args.steps, 2000))
+    r = cpu_arm(B, D, C, 0, steps=steps, warmup=max(3, min(args.warmup, 20)))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": max(3, min(args.warmup, 20)), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "B_per_gpu": B, "D": D, "C": C,
+                       "note": "CPU arm: one process on the host cores, not sharded over GPUs"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    B, D, C = (int(v) for v in args.shape.split(","))
+    if args.impl == "reference":
+        return run_reference(args, B, D, C)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from iif_b200 import histogram, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    # ---- synthetic inputs: X~N(0,1), W~U(+-1/sqrt(D)), b=0.01, long-tailed labels r=100
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    cnt = np.array([max(int(1280 * (0.01) ** (c / max(C - 1.0, 1.0))), 1) for c in range(C)], np.int64)
+    counts = torch.from_numpy(cnt).to(dev)
+    iif = histogram.iif_weights(counts, args.variant).reshape(-1).contiguous()
+    per_set = (B * D * 2 + C * D * 2 + B * 8) + (B * C * 4 + B * ops.pad8(C) * 2 + B * D * 2 + (C * D + C) * 4)
+    S = max(2, int(-(-2.0 * L2_BYTES // per_set)))           # rotating sets: footprint >= 2 x L2
+    prob = torch.from_numpy(cnt / cnt.sum())
+    sets = []
+    for s in range(S):
+        x = torch.randn(B, D, generator=g).to(dev).to(torch.bfloat16)
+        w = ((torch.rand(C, D, generator=g) * 2 - 1) / D ** 0.5).to(dev).to(torch.bfloat16)
+        y = torch.multinomial(prob, B, replacement=True, generator=g).to(dev)
+        bias = torch.full((C,), 0.01, device=dev)
+        hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True)
+        hs.bind(x, w, bias, iif, y)
+        sets.append(hs)
+    launches_per_step = sets[0].launches_per_step
+    cur = torch.cuda.current_stream(dev)
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+    ar_done = [None] * S
+
+    # ---- CUDA graphs: one per set (the kernels of one step); the all-reduce stays outside
+    graphs = [None] * S
+    use_graph = not args.no_graph
+    if use_graph:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for hs in sets:           # warm: module load, cudaFuncSetAttribute, tensor-map cache
+                hs.launch()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for i, hs in enumerate(sets):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                hs.launch()
+            graphs[i] = gph
+        torch.cuda.synchronize(dev)
+
+    def step(i):
+        k = i % S
+        if world > 1 and ar_done[k] is not None:
+            cur.wait_event(ar_done[k])            # the set's gradient buffer is free again
+        if use_graph:
+            graphs[k].replay()
+        else:
+            sets[k].launch()
+        if world > 1:
+            if args.sync_allreduce:
+                dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
+            else:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
+                    done = torch.cuda.Event()
+                    done.record(comm)
+                ar_done[k] = done
+
+    def fence():
+        if world > 1:
+            cur.wait_stream(comm)
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    fence()
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(cur)
+        for i in range(args.steps):
+            step(i)
+        if world > 1:
+            cur.wait_stream(comm)
+        e1.record(cur)
+        fence()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launched = ops.launch_count() - n0
+    gpu_launches = args.steps * launches_per_step if use_graph else launched
+    value = world * B * args.steps / (ms * 1e-3)
+    loss_val = float(sets[(args.steps - 1) % S].loss)
+
+    # ---- e2e: public API call with HOST (pinned) inputs; H2D of x,y and D2H of the loss every step
+    hx = [torch.randn(B, D, generator=g).to(torch.bfloat16).pin_memory() for _ in range(4)]
+    hy = [torch.multinomial(prob, B, replacement=True, generator=g).pin_memory() for _ in range(4)]
+    hloss = torch.zeros((), dtype=torch.float32).pin_memory()
+    xs = [hs._keep[0] for hs in sets]
+    ys = [hs._keep[4] for hs in sets]
+
+    def e2e_step(i):
+        k = i % S
+        xs[k].copy_(hx[i % 4], non_blocking=True)
+        ys[k].copy_(hy[i % 4], non_blocking=True)
+        step(i)
+        hloss.copy_(sets[k].loss, non_blocking=True)
+        cur.synchronize()
+        return float(hloss)
+
+    n_e2e = min(args.steps, 3000)
+    for i in range(10):
+        e2e_step(i)
+    fence()
+    t0 = time.perf_counter()
+    e0.record(cur)
+    for i in range(n_e2e):
+        e2e_step(i)
+    if world > 1:
+        cur.wait_stream(comm)
+    e1.record(cur)
+    fence()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, wall_ms)      # host-synchronised loop: wall clock and events agree; keep the larger
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": world * B * n_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * D * 2 + B * 8,
+           "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e}
+
+    # ---- per-kernel timing (rank 0): each kernel of the step alone, back to back over the rotating sets
+    pk = peaks()
+    kern = []
+    if rank == 0:
+        e = 2
+        algo = {  # algorithmic bytes / flops per launch
+            "linear_fwd_bf16": (e * (B * D + C * D) + 4 * B * C + 4 * C, 2.0 * B * D * C),
+            "softmax_ce_fwd_bwd": (4 * B * C + 2 * B * C + 8 * B + 8 * B + 4 * C, 0.0),
+            "colsum_db": (2 * B * C + 4 * C, 0.0),
+            "linear_bwd_dx_bf16": (2 * B * C + e * C * D + e * B * D, 2.0 * B * D * C),
+            "linear_bwd_dw_bf16": (2 * B * C + e * B * D + 4 * C * D, 2.0 * B * D * C),
+        }
+        names = [n for n, _ in sets[0].kernels()]
+        reps = max(1, 600 // S)
+        for j, name in enumerate(names):
+            fns = [hs.kernels()[j][1] for hs in sets]
+            for f in fns:
+                f()
+            torch.cuda.synchronize(dev)
+            e0.record(cur)
+            for _ in range(reps):
+                for f in fns:
+                    f()
+            e1.record(cur)
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / (reps * S)
+            by, fl = algo[name]
+            t_hbm, t_tc = by / (pk["hbm"] * 1e9), fl / (pk["tf_burst"] * 1e12)
+            bound = "hbm" if t_hbm >= t_tc else "tensor"
+            ach = by / (us * 1e-6) / 1e9 if bound == "hbm" else fl / (us * 1e-6) / 1e12
+            peak = pk["hbm"] if bound == "hbm" else pk["tf_burst"]
+            kern.append({"kernel": name, "us": us, "bound": bound, "achieved": ach, "peak": peak,
+                         "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak, "algo_bytes": by,
+                         "flops": fl})
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        tot = sum(k["us"] for k in kern)
+        for k in kern:
+            k["share"] = k["us"] / tot
+        top = max(kern, key=lambda k: k["us"])
+        roofline = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                    "frac": top["frac"], "traffic": None, "kernel": top["kernel"], "us_per_launch": top["us"],
+                    "peak_source": pk["src"] + (" burst" if top["bound"] == "tensor" else " copy"),
+                    "step_roofline_us": sum(max(k["algo_bytes"] / (pk["hbm"] * 1e9), k["flops"] / (pk["tf_sust"] * 1e12))
+                                            for k in kern) * 1e6}
+        roofline["step_frac"] = roofline["step_roofline_us"] / (ms * 1e3 / args.steps)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_arm(B, D, C, args.cpu_seconds)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD if (B, D, C) == (256, 2048, 1000) else f"IIF head {B}x{D}x{C}",
+                           "B_per_gpu": B, "D": D, "C": C, "global_batch": B * world, "variant": args.variant,
+                           "parallelism": f"dp{world} (row sharding, NCCL all-reduce(mean) of dW+db "
+                                          f"{'on the compute stream' if args.sync_allreduce else 'overlapped on a side stream'})"
+                                          if world > 1 else "dp1",
+                           "launch": "cuda-graph replay (one graph per step)" if use_graph else "eager",
+                           "l2": f"rotating {S} independent input+output sets, {S * per_set / 1e6:.0f} MB > 126 MB L2"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+                "kernels": kern, "cpu_baseline": cpu, "loss": loss_val}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -334,7 +334,8 @@ class HeadStep:
     """Pre-allocated buffers + one C call (`iif_head_fwd_bwd_bf16`) per head step.
 
     fc_cls -> IIF softmax-CE fwd+bwd -> db, dX, dW with bf16 GEMM operands.  Buffers are allocated
-    once so the step can be captured in a CUDA graph."""
+    once so the step can be captured in a CUDA graph.  dW and db live in ONE flat fp32 buffer
+    (`grad_flat`) so the data-parallel all-reduce of the head's parameter gradients is one message."""
 
     def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False):
         dev = torch.device(device)
@@ -345,8 +346,9 @@ class HeadStep:
         self.loss = torch.zeros((), dtype=f32, device=dev)
         self.dz = torch.empty(B, pad8(Cc), dtype=torch.bfloat16, device=dev)
         self.dx = torch.empty(B, D, dtype=torch.bfloat16 if dx_bf16 else f32, device=dev) if need_dx else None
-        self.dw = torch.empty(Cc, D, dtype=f32, device=dev)
-        self.db = torch.empty(Cc, dtype=f32, device=dev) if need_db else None
+        self.grad_flat = torch.empty(Cc * D + (Cc if need_db else 0), dtype=f32, device=dev)
+        self.dw = self.grad_flat[:Cc * D].view(Cc, D)
+        self.db = self.grad_flat[Cc * D:] if need_db else None
         self.argmax = torch.empty(B, dtype=i32, device=dev) if want_acc else None
         self.rank = torch.empty(B, dtype=i32, device=dev) if want_acc else None
         self.acc_counts = torch.zeros(2, dtype=i32, device=dev) if want_acc else None
@@ -356,9 +358,13 @@ class HeadStep:
         self.ws_bytes = n
         self.dx_dtype = _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32
         self.launches_per_step = 3 + (1 if need_dx else 0) + (1 if need_db else 0)
+        self._args = None
+        self._keep = None
 
-    def run(self, x, w, bias, iif, label, *, class_weight=None, sample_weight=None, ignore_index=-100,
-            scale=None):
+    def bind(self, x, w, bias, iif, label, *, class_weight=None, sample_weight=None, ignore_index=-100,
+             scale=None):
+        """Fix the input tensors of this step (their storage must stay alive and in place; new values
+        are copied INTO them).  Fills the C argument struct once; `launch()` then costs one C call."""
         B, D, Cc = self.B, self.D, self.C
         _cuda(x, "x", torch.bfloat16)
         _cuda(w, "w", torch.bfloat16)
@@ -367,6 +373,10 @@ class HeadStep:
             raise ValueError("HeadStep: shape mismatch")
         if x.stride(1) != 1 or w.stride(1) != 1:
             raise ValueError("HeadStep: x and w need unit inner stride")
+        bias = _vec(bias, "bias", Cc)
+        iif = _vec(iif, "iif", Cc)
+        class_weight = _vec(class_weight, "class_weight", Cc)
+        sample_weight = _vec(sample_weight, "sample_weight", B)
         a = _lib.HeadArgs()
         a.x, a.ldx, a.w, a.ldw = x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0)
         a.bias = None if bias is None else bias.data_ptr()
@@ -389,5 +399,42 @@ class HeadStep:
         a.acc_counts = None if self.acc_counts is None else self.acc_counts.data_ptr()
         a.ticket = self.ticket.data_ptr()
         a.ws, a.ws_bytes = self.ws.data_ptr(), self.ws_bytes
-        _lib.check(_lib.load().iif_head_fwd_bwd_bf16(C.byref(a), _stream(self.device)), "head_fwd_bwd_bf16")
+        self._args = a
+        self._keep = (x, w, bias, iif, label, class_weight, sample_weight)
+        self._fn = _lib.load().iif_head_fwd_bwd_bf16
+        return self
+
+    def launch(self):
+        """Enqueue the bound step on the current stream; returns the 0-dim device loss."""
+        rc = self._fn(C.byref(self._args), _stream(self.device))
+        if rc:
+            _lib.check(rc, "head_fwd_bwd_bf16")
         return self.loss
+
+    def run(self, x, w, bias, iif, label, **kw):
+        self.bind(x, w, bias, iif, label, **kw)
+        return self.launch()
+
+    def kernels(self):
+        """The individual launches of the bound step as (name, callable) pairs -- same buffers, same C
+        entry points as `launch()`; used by bench.py to time each kernel on its own."""
+        lib, a = _lib.load(), self._args
+        st = lambda: _stream(self.device)
+        p = C.c_void_p
+        out = [("linear_fwd_bf16", lambda: lib.iif_linear_fwd_bf16(p(a.x), a.ldx, p(a.w), a.ldw, p(a.bias), None,
+                                                                   p(a.z), a.ldz, None, 0, a.B, a.D, a.C, p(a.ws),
+                                                                   a.ws_bytes, st())),
+               ("softmax_ce_fwd_bwd", lambda: lib.iif_softmax_ce_fwd_bwd(
+                   p(a.z), a.ldz, p(a.iif), p(a.label), p(a.class_weight), p(a.sample_weight), a.ignore_index, a.scale,
+                   a.B, a.C, p(a.loss_i), p(a.loss_sum), None, 0, p(a.dz_bf16), a.lddz, None, p(a.argmax), p(a.rank),
+                   p(a.acc_counts), p(a.ticket), st()))]
+        if self.db is not None:
+            out.append(("colsum_db", lambda: lib.iif_colsum(p(a.dz_bf16), _lib.DTYPE_BF16, a.lddz, None, a.B, a.C,
+                                                            p(a.db), st())))
+        if self.dx is not None:
+            out.append(("linear_bwd_dx_bf16", lambda: lib.iif_linear_bwd_dx_bf16(
+                p(a.dz_bf16), a.lddz, p(a.w), a.ldw, None, p(a.dx), a.dx_dtype, a.lddx, a.B, a.D, a.C, p(a.ws),
+                a.ws_bytes, st())))
+        out.append(("linear_bwd_dw_bf16", lambda: lib.iif_linear_bwd_dw_bf16(
+            p(a.dz_bf16), a.lddz, p(a.x), a.ldx, None, p(a.dw), a.lddw, a.B, a.D, a.C, p(a.ws), a.ws_bytes, st())))
+        return out

@@ -1,0 +1,299 @@
+"""GPU parity of the drop-in modules (the reference's own API surface) against the golden vectors
+produced by the unmodified reference Python and against the float64 oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import head_oracle as ho
+from tests._common import TOL_F32, TOL_BF16, rel_err, head_inputs, iif_row, bf16_round
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def T(a, dtype=None):
+    t = torch.as_tensor(np.asarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def N(t):
+    return t.detach().float().cpu().numpy()
+
+
+class _DS:
+    def __init__(self, counts):
+        self.counts = [int(c) for c in counts]
+
+    def get_cls_num_list(self):
+        return self.counts
+
+
+# ------------------------------------------------------------------ classification/custom.py surface
+@pytest.mark.parametrize("tag", [f"{v}_mean" for v in ho.VARIANTS] + ["raw_sum", "raw_none", "smooth_sum"])
+def test_cls_iifloss_module(golden, tag):
+    from iif_b200.classification import IIFLoss
+    from iif_b200 import functional as F_
+    g = golden("cls_iif")
+    v, red = tag.rsplit("_", 1)
+    crit = IIFLoss(_DS(g["counts"]), variant=v, reduction=red, device=DEV)
+    assert hasattr(crit, "iif") and set(crit.iif) == set(ho.VARIANTS) and crit.iif[v].shape == (1, 10)
+    x = T(g["x"]).requires_grad_(True)
+    w = T(g["w"]).requires_grad_(True)
+    b = T(g["b"]).requires_grad_(True)
+    out = F_.linear(x, w, b)                      # fp32 parity mode of fc
+    assert rel_err(N(out), g["z"]) < TOL_F32
+    loss = crit(out, T(g["y"]))
+    if red == "none":
+        assert rel_err(N(loss), g[f"loss_{tag}"]) < TOL_F32
+        loss.sum().backward()
+    else:
+        assert float(loss) == pytest.approx(float(g[f"loss_{tag}"]), rel=TOL_F32)
+        loss.backward()
+    assert rel_err(N(x.grad), g[f"dx_{tag}"]) < TOL_F32
+    assert rel_err(N(w.grad), g[f"dw_{tag}"]) < TOL_F32
+    assert rel_err(N(b.grad), g[f"db_{tag}"]) < TOL_F32
+    if red == "mean":
+        assert np.array_equal(N(crit(out.detach(), infer=True)), g[f"infer_{v}"])
+
+
+def test_cls_iifloss_class_weight_norm_and_mixup(golden):
+    from iif_b200.classification import IIFLoss, Mixup
+    g = golden("cls_iif")
+    z = T(g["z"]).requires_grad_(True)
+    crit = IIFLoss(_DS(g["counts"]), variant="smooth", device=DEV, weight=T(g["cw"]))
+    loss = crit(z, T(g["y"]))
+    assert float(loss) == pytest.approx(float(g["loss_smooth_cw_mean"]), rel=TOL_F32)
+    crit = IIFLoss(_DS(g["counts"]), variant="raw", iif_norm=2, device=DEV)
+    assert rel_err(N(crit.iif["raw"]), g["iifn2_raw"]) < 1e-6
+    z2 = T(g["z"]).requires_grad_(True)
+    loss = crit(z2, T(g["y"]))
+    assert float(loss) == pytest.approx(float(g["loss_raw_n2_mean"]), rel=TOL_F32)
+    loss.backward()
+    assert rel_err(N(z2.grad), g["dz_raw_n2_mean"]) < TOL_F32
+    # Mixup.mixup_criterion: lam * crit(p, ya) + (1 - lam) * crit(p, yb)  (custom.py:116-117)
+    mx = Mixup(crit)
+    yb = T(np.roll(g["y"], 3))
+    z3 = T(g["z"]).requires_grad_(True)
+    lm = mx.mixup_criterion(z3, T(g["y"]), yb, 0.3)
+    la, dza, _ = ho.softmax_ce(g["z"], g["iifn2_raw"], g["y"])
+    lb, dzb, _ = ho.softmax_ce(g["z"], g["iifn2_raw"], np.roll(g["y"], 3))
+    assert float(lm) == pytest.approx(0.3 * la.mean() + 0.7 * lb.mean(), rel=TOL_F32)
+    lm.backward()
+    assert rel_err(N(z3.grad), (0.3 * dza + 0.7 * dzb) / len(la)) < TOL_F32
+
+
+def test_cls_focal_gamma0_and_accuracy(golden):
+    from iif_b200.classification import FocalLoss, accuracy, predictions
+    g = golden("cls_bce")
+    for tag, w in (("now", None), ("w", g["weights"])):
+        for red in ("mean", "sum"):
+            z = T(g["z"]).requires_grad_(True)
+            crit = FocalLoss(0, reduction=red, weights=None if w is None else T(w))
+            loss = crit(z, T(g["y"]))
+            assert float(loss) == pytest.approx(float(g[f"loss_{tag}_{red}"]), rel=TOL_F32)
+            loss.backward()
+            assert rel_err(N(z.grad), g[f"dz_{tag}_{red}"]) < TOL_F32
+    with pytest.raises(NotImplementedError):
+        FocalLoss(2.0)
+    c = golden("cls_iif")
+    a1, a5 = accuracy(T(c["z"]), T(c["y"]), topk=(1, 5))
+    e1, e5 = ho.topk_accuracy(c["z"], c["y"], (1, 5))
+    assert float(a1) == pytest.approx(e1, abs=1e-4) and float(a5) == pytest.approx(e5, abs=1e-4)
+    assert np.array_equal(predictions(T(c["z"])).cpu().numpy(), ho.argmax_first(c["z"]))
+    assert np.array_equal(predictions(T(c["z"]), T(c["iif_raw"])).cpu().numpy(),
+                          ho.argmax_first((c["z"] * c["iif_raw"]).astype(np.float32)))
+
+
+def test_cls_rejects_cpu():
+    from iif_b200.classification import IIFLoss
+    from iif_b200 import ops
+    with pytest.raises(RuntimeError):
+        IIFLoss(_DS([5, 3]), device="cpu")
+    with pytest.raises(RuntimeError):
+        ops.softmax_ce(torch.zeros(2, 3), None, torch.zeros(2, dtype=torch.int64))
+
+
+# ------------------------------------------------------------------ mmdet surface
+@pytest.fixture(scope="module")
+def csv1204(golden, tmp_path_factory):
+    """Rebuild idf_1204.csv from the frozen columns (the reference tree is absent on the GPU box)."""
+    import pandas as pd
+    g = golden("weight_tables")
+    cols = {k[len("idf_1204_"):]: g[k] for k in g if k.startswith("idf_1204_") and g[k].shape == (1204,)}
+    p = tmp_path_factory.mktemp("csv") / "idf_1204.csv"
+    pd.DataFrame(cols).to_csv(p, index=False, float_format="%.17g")
+    return str(p)
+
+
+def test_mmdet_iifloss(golden, csv1204):
+    from iif_b200 import mmdet as M
+    g = golden("mmdet_iif")
+    af = float(g["avg_factor"])
+    crit = M.IIFLoss(num_classes=1203, path=csv1204, variant="raw")
+    assert crit.custom_cls_channels and crit.custom_activation and crit.custom_accuracy
+    assert crit.get_cls_channels(1203) == 1204
+    with pytest.raises(AssertionError):
+        crit.get_cls_channels(80)
+    with pytest.raises(AssertionError):
+        M.IIFLoss(use_sigmoid=True, path=csv1204)
+    with pytest.raises(KeyError):
+        M.IIFLoss(path=csv1204, variant="log_adj")
+    assert np.array_equal(N(crit.iif_weights), g["iif_raw"])
+
+    def run(tag, rows=None, **kw):
+        z = T(g["z"]).requires_grad_(True)
+        loss = crit(z, T(g["y"]), **kw)
+        ref = g[f"loss_{tag}"]
+        if ref.ndim:
+            assert rel_err(N(loss), ref) < TOL_F32
+            loss.sum().backward()
+        else:
+            assert float(loss) == pytest.approx(float(ref), rel=TOL_F32)
+            loss.backward()
+        assert rel_err(N(z.grad)[:rows], g[f"dz_{tag}"]) < TOL_F32
+
+    run("raw_avg", rows=8, weight=T(g["w"]), avg_factor=af)
+    run("raw_plain")
+    run("raw_w_mean", weight=T(g["w"]))
+    run("raw_none", weight=T(g["w"]), reduction_override="none")
+    run("raw_sum", weight=T(g["w"]), reduction_override="sum")
+    run("raw_none_avg", weight=T(g["w"]), avg_factor=af, reduction_override="none")
+    with pytest.raises(ValueError):
+        crit(T(g["z"]), T(g["y"]), avg_factor=af, reduction_override="sum")      # losses/utils.py:53-54
+    with pytest.raises(AssertionError):
+        crit(T(g["z"]), T(g["y"]), reduction_override="bogus")                   # iif_loss.py:132
+    # activation / accuracy
+    assert rel_err(N(crit.get_activation(T(g["z"]))), g["act_raw"]) < TOL_F32
+    acc = crit.get_accuracy(T(g["z"]), T(g["y"]))
+    assert np.float32(float(acc["acc_classes"])) == pytest.approx(float(g["acc_raw"][0]), abs=1e-4)
+    # empty batch (tests/test_models/test_loss.py:88-101)
+    e = crit(torch.zeros(0, 1204, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), avg_factor=1.0)
+    assert isinstance(e, torch.Tensor) and float(e) == 0.0
+    # loss_weight + class_weight variant
+    crit2 = M.IIFLoss(num_classes=1203, path=csv1204, variant="smooth", loss_weight=0.5,
+                      class_weight=[float(v) for v in g["class_weight"]])
+    z = T(g["z"]).requires_grad_(True)
+    loss = crit2(z, T(g["y"]), weight=T(g["w"]), avg_factor=af)
+    assert float(loss) == pytest.approx(float(g["loss_smooth_cw_lw"]), rel=TOL_F32)
+
+
+def test_mmdet_fasa_and_ce(golden, csv1204):
+    from iif_b200 import mmdet as M
+    g = golden("mmdet_iif")
+    af = float(g["avg_factor"])
+    crit = M.FasaIIFLoss(use_sigmoid=True, num_classes=1203, path=csv1204, variant="base10_obj")
+    z = T(g["z"]).requires_grad_(True)
+    loss = crit(z, T(g["y"]), weight=T(g["w"]), avg_factor=af)           # sigmoid: NO iif (fasa_iif_loss.py:35-36)
+    assert float(loss) == pytest.approx(float(g["loss_fasa_sigmoid_avg"]), rel=TOL_F32)
+    loss.backward()
+    assert rel_err(N(z.grad), g["dz_fasa_sigmoid_avg"]) < TOL_F32
+    assert rel_err(N(crit.get_activation(T(g["z"]))), g["fasa_act"]) < TOL_F32   # ...but activation does
+    # cums (fasa_iif_loss.py:60-71,154-160)
+    crit = M.FasaIIFLoss(num_classes=1203, path=csv1204, variant="raw", use_cums=True)
+    yc = T(np.maximum(g["y"], 0))
+    rets = [float(crit(T(zz), yc)) for zz in (g["z"], g["z"] * 0.5)]
+    assert rel_err(np.array(rets), g["fasa_cum_ret"]) < TOL_F32
+    assert rel_err(N(crit.cum_losses), g["fasa_cum_losses"]) < TOL_F32
+    assert np.array_equal(N(crit.cum_labels), g["fasa_cum_labels"])
+    crit.close_cums()
+    assert crit.reduction == "mean" and not N(crit.cum_labels).any()
+    # plain CrossEntropyLoss softmax / sigmoid (cross_entropy_loss.py:165-249)
+    b = golden("mmdet_bce")
+    afb = float(b["avg_factor"])
+    ce = M.CrossEntropyLoss(use_sigmoid=True)
+    for tag, kw in (("plain", {}), ("avg", dict(weight=T(b["w"]), avg_factor=afb)),
+                    ("ign255_avg", dict(weight=T(b["w"]), avg_factor=afb, ignore_index=255)),
+                    ("none", dict(weight=T(b["w"]), reduction_override="none")),
+                    ("sum", dict(weight=T(b["w"]), reduction_override="sum"))):
+        z = T(b["z"]).requires_grad_(True)
+        loss = ce(z, T(b["y"]), **kw)
+        if b[f"loss_{tag}"].ndim:
+            assert rel_err(N(loss), b[f"loss_{tag}"]) < TOL_F32
+            loss.sum().backward()
+        else:
+            assert float(loss) == pytest.approx(float(b[f"loss_{tag}"]), rel=TOL_F32)
+            loss.backward()
+        assert rel_err(N(z.grad), b[f"dz_{tag}"]) < TOL_F32
+    ce2 = M.CrossEntropyLoss(use_sigmoid=True, class_weight=[float(v) for v in b["pos_weight"]], loss_weight=2.0)
+    loss = ce2(T(b["z"]), T(b["y"]), weight=T(b["w"]), avg_factor=afb)
+    assert float(loss) == pytest.approx(float(b["loss_pw_lw_avg"]), rel=TOL_F32)
+    ce3 = M.CrossEntropyLoss()
+    z = T(b["ce_z"]).requires_grad_(True)
+    loss = ce3(z, T(b["ce_y"]), weight=T(b["w"]), avg_factor=afb)
+    assert float(loss) == pytest.approx(float(b["ce_loss"]), rel=TOL_F32)
+    loss.backward()
+    assert rel_err(N(z.grad), b["ce_dz"]) < TOL_F32
+
+
+def test_mmdet_accuracy_kat():
+    """seg/tests/test_metrics/test_losses.py:186-240."""
+    from iif_b200.mmdet import accuracy, Accuracy
+    pred = T(np.array([[0.2, 0.3, 0.6, 0.5], [0.1, 0.1, 0.2, 0.6], [0.9, 0.0, 0.0, 0.1],
+                       [0.4, 0.7, 0.1, 0.1], [0.0, 0.0, 0.99, 0]], np.float32))
+    t1 = T(np.array([2, 3, 0, 1, 2], np.int64))
+    assert float(Accuracy(topk=1)(pred, t1)) == 100
+    assert float(Accuracy(topk=1, thresh=0.8)(pred, t1)) == 40
+    assert float(Accuracy(topk=2)(pred, T(np.array([3, 2, 0, 0, 2], np.int64)))) == 100
+    a = accuracy(pred, t1, topk=(1, 2))
+    assert [float(v) for v in a] == [100.0, 100.0]
+    assert float(accuracy(torch.zeros(0, 4, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV))) == 0
+    with pytest.raises(AssertionError):
+        accuracy(pred, t1, topk=5)
+
+
+def test_mmdet_linear_fc_cls():
+    """fc_cls as an nn.Linear subclass: fp32 parity mode at 1e-5, bf16 tcgen05 mode at 2e-2; .grad
+    produced by autograd so DDP hooks fire."""
+    from iif_b200.mmdet import Linear
+    x, w, b, counts, y = head_inputs(512, 1024, 1204, seed=4, relu=True)
+    rng = np.random.default_rng(0)
+    gz = (rng.standard_normal((512, 1204)) / 512).astype(np.float32)
+    zr = ho.linear_fwd(x, w, b)
+    dxr, dwr, dbr = ho.linear_bwd(gz, x, w)
+    for compute, tol in (("fp32", TOL_F32), ("bf16", TOL_BF16)):
+        fc = Linear(1024, 1204, compute=compute).to(DEV)
+        assert isinstance(fc, torch.nn.Linear) and set(dict(fc.named_parameters())) == {"weight", "bias"}
+        with torch.no_grad():
+            fc.weight.copy_(T(w)); fc.bias.copy_(T(b))
+        xt = T(x).requires_grad_(True)
+        z = fc(xt)
+        assert rel_err(N(z), zr) < tol
+        z.backward(T(gz))
+        assert rel_err(N(xt.grad), dxr) < tol
+        assert rel_err(N(fc.weight.grad), dwr) < tol
+        assert rel_err(N(fc.bias.grad), dbr) < tol
+
+
+# ------------------------------------------------------------------ fused head (bf16 GEMM mode)
+@pytest.mark.parametrize("B,D,C,relu", [(256, 2048, 1000, False), (256, 2048, 365, False), (1024, 1024, 1204, True),
+                                        (128, 64, 10, False)])
+def test_fused_head_bf16(B, D, C, relu):
+    from iif_b200 import functional as F_
+    from iif_b200.ops import HeadStep
+    x, w, b, counts, y = head_inputs(B, D, C, seed=C, relu=relu)
+    iif = iif_row(counts, "smooth")
+    ref32 = ho.head_fwd_bwd(x, w, b, iif, y)
+    ref16 = ho.head_fwd_bwd(bf16_round(x), bf16_round(w), b, iif, y)
+    xt = T(x).requires_grad_(True)
+    wt = T(w).requires_grad_(True)
+    bt = T(b).requires_grad_(True)
+    loss, z = F_.iif_head_loss(xt, wt, bt, T(iif), T(y))
+    loss.backward()
+    for ref, tol in ((ref16, 6e-3), (ref32, TOL_BF16)):     # 6e-3: bf16 storage of dZ
+        assert float(loss) == pytest.approx(ref["loss"], rel=tol)
+        assert rel_err(N(z), ref["z"]) < tol
+        assert rel_err(N(xt.grad), ref["dx"]) < tol
+        assert rel_err(N(wt.grad), ref["dw"]) < tol
+        assert rel_err(N(bt.grad), ref["db"]) < tol
+    # one-call C entry point with pre-allocated buffers (the bench path)
+    hs = HeadStep(B, D, C, DEV, want_acc=True, dx_bf16=False)
+    l2 = hs.run(T(x, torch.bfloat16), T(w, torch.bfloat16), T(b), T(iif).reshape(-1), T(y))
+    torch.cuda.synchronize()
+    assert float(l2) == pytest.approx(ref16["loss"], rel=1e-4)
+    assert rel_err(N(hs.dw), ref16["dw"]) < 6e-3 and rel_err(N(hs.dx), ref16["dx"]) < 6e-3
+    assert rel_err(N(hs.db), ref16["db"]) < 6e-3
+    assert np.array_equal(hs.argmax.cpu().numpy(), ho.argmax_first(N(hs.z)))      # bit-exact on its own logits
+    assert np.array_equal(hs.rank.cpu().numpy(), ho.label_rank(N(hs.z), y))

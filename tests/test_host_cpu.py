@@ -1,0 +1,120 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol that
+include/iif_b200.h declares, the ctypes mirror matches the C struct layout, host-side helper
+logic (reductions, error conventions, the shared ndtri restatement) -- no compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "iif_b200.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"IIF_API\s+[\w\s\*]+?\b(iif_\w+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    names = header_symbols()
+    for n in ("iif_hist_labels_i64", "iif_hist_images_dedup_i64", "iif_weights_from_counts", "iif_softmax_ce_fwd_bwd",
+              "iif_sigmoid_bce_fwd_bwd", "iif_scaled_activation", "iif_linear_fwd_bf16", "iif_linear_fwd_f32",
+              "iif_linear_bwd_dx_bf16", "iif_linear_bwd_dw_bf16", "iif_head_fwd_bwd_bf16"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    from iif_b200 import _lib
+    lib = _lib.load()
+    names = header_symbols()
+    assert sorted(_lib.SIGNATURES) == names          # ctypes mirror and header agree one to one
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.iif_abi_version() == 1
+    assert b"alignment" in lib.iif_error_string(-2)
+    assert lib.iif_gemm_ws_bytes(0, 2048, 1000) == 0
+    assert lib.iif_gemm_ws_bytes(256, 2048, 1000) > 0
+    assert lib.iif_hist_images_dedup_ws_bytes(100, 10) == 10 * 4 * 4
+    # no stray exports: only the iif_* C ABI is visible
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert sorted(exported) == names
+
+
+def test_head_args_struct_layout(tmp_path):
+    """ctypes HeadArgs == struct iif_head_args as gcc lays it out."""
+    from iif_b200 import _lib
+    fields = [f[0] for f in _lib.HeadArgs._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(){",
+            'printf("%zu\\n", sizeof(iif_head_args));']
+    prog += [f'printf("%zu\\n", offsetof(iif_head_args, {f}));' for f in fields]
+    prog += ["return 0;}"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", str(c), "-o", str(exe)], check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert vals[0] == ctypes.sizeof(_lib.HeadArgs)
+    assert vals[1:] == [getattr(_lib.HeadArgs, f).offset for f in fields]
+
+
+def test_ndtri_host_matches_scipy(tmp_path):
+    """csrc/ndtri.h (the Cephes restatement shared with the CUDA weight kernel) against
+    scipy.special.ndtri -- the function the reference calls (classification/custom.py:4,20)."""
+    from scipy.special import ndtri
+    c = tmp_path / "nd.c"
+    c.write_text(f'#include "{os.path.join(ROOT, "iif_b200", "csrc", "ndtri.h")}"\n'
+                 "double nd(double y){return iif_ndtri(y);}\n")
+    so = tmp_path / "nd.so"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", str(c), "-o", str(so), "-lm"], check=True)
+    f = ctypes.CDLL(str(so)).nd
+    f.restype, f.argtypes = ctypes.c_double, [ctypes.c_double]
+    rng = np.random.default_rng(0)
+    ys = np.concatenate([rng.uniform(0, 1, 4000), 10.0 ** rng.uniform(-300, -1, 2000),
+                         1 - 10.0 ** rng.uniform(-15, -1, 1000), [0.5, 0.1353352832366127, 0.8646647167633873]])
+    got = np.array([f(float(y)) for y in ys])
+    ref = ndtri(ys)
+    np.testing.assert_allclose(got, ref, rtol=4e-15, atol=1e-300)
+    assert f(0.0) == -np.inf and f(1.0) == np.inf and np.isnan(f(1.5))
+
+
+def test_mmdet_reduction_contract():
+    """losses/utils.py:42-55 folded into (scale, reduce?)."""
+    from iif_b200.mmdet import _resolve, _empty_result
+    assert _resolve("mean", None, 1.0, 8) == (1 / 8, True)
+    assert _resolve("sum", None, 2.0, 8) == (2.0, True)
+    assert _resolve("none", None, 1.0, 8) == (1.0, False)
+    assert _resolve("mean", 4.0, 0.5, 8) == (0.125, True)
+    assert _resolve("none", 4.0, 1.0, 8) == (1.0, False)
+    with pytest.raises(ValueError, match="avg_factor can not be used"):
+        _resolve("sum", 4.0, 1.0, 8)
+    e = torch.zeros(0, 5)
+    assert _empty_result(e, "none", None).shape == (0,)
+    assert torch.isnan(_empty_result(e, "mean", None))             # torch: mean of empty
+    assert float(_empty_result(e, "mean", 3.0)) == 0.0 and float(_empty_result(e, "sum", None)) == 0.0
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA tensors -- never route through a CPU path."""
+    from iif_b200 import ops
+    z = torch.zeros(4, 8)
+    y = torch.zeros(4, dtype=torch.int64)
+    for call in (lambda: ops.softmax_ce(z, None, y), lambda: ops.sigmoid_bce(z, y),
+                 lambda: ops.scaled_activation(z, None, True), lambda: ops.hist_labels(y, 8),
+                 lambda: ops.linear_fwd(z, torch.zeros(3, 8)), lambda: ops.colsum(z)):
+        with pytest.raises(RuntimeError, match="CUDA tensor"):
+            call()
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under iif_b200/ may import it."""
+    pkg = os.path.join(ROOT, "iif_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f

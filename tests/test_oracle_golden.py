@@ -243,3 +243,29 @@ def test_shot_accuracy():
     preds = np.array([0, 0, 1, 2, 2, 1])
     labels = np.array([0, 0, 1, 2, 2, 2])
     assert ho.shot_accuracy(preds, labels, [500, 50, 5]) == (1.0, 1.0, pytest.approx(2 / 3))
+
+
+# ------------------------------------------------------------------ torch CPU port (the bench's CPU arm)
+@pytest.mark.parametrize("tag", ["raw_mean", "smooth_mean", "normit_mean", "raw_sum", "smooth_none"])
+def test_torch_port_cls(golden, tag):
+    import torch
+    from oracle import torch_port as tp
+    g = golden("cls_iif")
+    v, red = tag.rsplit("_", 1)
+    t = lambda k: torch.from_numpy(g[k])
+    r = tp.head_step(t("x"), t("w"), t("b"), t(f"iif_{v}"), t("y"), reduction=red)
+    close(r["loss"].numpy(), g[f"loss_{tag}"])
+    for k in ("dx", "dw", "db"):
+        close(r[k].numpy(), g[f"{k}_{tag}"])
+
+
+def test_torch_port_mmdet(golden):
+    import torch
+    from oracle import torch_port as tp
+    g = golden("mmdet_iif")
+    z = torch.from_numpy(g["z"])
+    eye = torch.eye(z.shape[1])
+    r = tp.head_step(z, eye, None, torch.from_numpy(g["iif_raw"]), torch.from_numpy(g["y"]),
+                     sample_weight=torch.from_numpy(g["w"]), avg_factor=float(g["avg_factor"]))
+    close(r["loss"].numpy(), g["loss_raw_avg"])
+    close(r["dx"].numpy()[:8], g["dz_raw_avg"])                       # W = I: dX is dZ
