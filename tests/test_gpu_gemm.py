@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import head_oracle as ho
-from tests._common import TOL_F32, TOL_BF16, rel_err, head_inputs, bf16_round
+from _common import TOL_F32, TOL_BF16, rel_err, head_inputs, bf16_round
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import head_oracle as ho
-from tests._common import lt_counts, lt_labels
+from _common import lt_counts, lt_labels
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

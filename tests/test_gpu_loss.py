@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import head_oracle as ho
-from tests._common import TOL_F32, TOL_BF16, rel_err, head_inputs, iif_row, lt_counts
+from _common import TOL_F32, TOL_BF16, rel_err, head_inputs, iif_row, lt_counts
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
