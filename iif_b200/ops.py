@@ -36,7 +36,8 @@ def _rows(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
 
 
 def _ld(t: torch.Tensor) -> int:
-    return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.shape[1]), 1)
+    """Leading dimension in elements.  A single row never steps by it: report an aligned value."""
+    return int(t.stride(0)) if t.shape[0] > 1 else (max(int(t.shape[1]), 1) + 7) // 8 * 8
 
 
 def _vec(t: Optional[torch.Tensor], name: str, n: int, dtype=torch.float32):

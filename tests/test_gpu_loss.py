@@ -115,7 +115,8 @@ def test_softmax_ce_cls_golden(ops, golden, tag):
 def test_softmax_ce_mmdet_golden(ops, golden):
     """Against the unmodified mmdet IIFLoss (all 14 CSV columns, avg_factor + label weights)."""
     g = golden("mmdet_iif")
-    cols = [k[len("loss_"):-len("_avg")] for k in g if k.startswith("loss_") and k.endswith("_avg") and "none" not in k]
+    base = ["smooth", "raw", "prob", "normit", "gombit", "base2", "base10"]
+    cols = base + [c + "_obj" for c in base]
     assert len(cols) == 14
     for col in cols:
         r = ops.softmax_ce(T(g["z"]), T(g[f"iif_{col}"]), T(g["y"]), sample_weight=T(g["w"]),
