@@ -176,12 +176,13 @@ def main():
     S = max(2, int(-(-2.0 * L2_BYTES // per_set)))           # rotating sets: footprint >= 2 x L2
     prob = torch.from_numpy(cnt / cnt.sum())
     sets = []
+    shared_ws = torch.empty(max(int(ops._lib.load().iif_gemm_ws_bytes(B, D, C)), 1), dtype=torch.uint8, device=dev)
     for s in range(S):
         x = torch.randn(B, D, generator=g).to(dev).to(torch.bfloat16)
         w = ((torch.rand(C, D, generator=g) * 2 - 1) / D ** 0.5).to(dev).to(torch.bfloat16)
         y = torch.multinomial(prob, B, replacement=True, generator=g).to(dev)
         bias = torch.full((C,), 0.01, device=dev)
-        hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True)
+        hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws)
         hs.bind(x, w, bias, iif, y)
         sets.append(hs)
     launches_per_step = sets[0].launches_per_step
@@ -303,9 +304,7 @@ def main():
         algo = {  # algorithmic bytes / flops per launch
             "linear_fwd_bf16": (e * (B * D + C * D) + 4 * B * C + 4 * C, 2.0 * B * D * C),
             "softmax_ce_fwd_bwd": (4 * B * C + 2 * B * C + 8 * B + 8 * B + 4 * C, 0.0),
-            "colsum_db": (2 * B * C + 4 * C, 0.0),
-            "linear_bwd_dx_bf16": (2 * B * C + e * C * D + e * B * D, 2.0 * B * D * C),
-            "linear_bwd_dw_bf16": (2 * B * C + e * B * D + 4 * C * D, 2.0 * B * D * C),
+            "linear_bwd_bf16": (2 * B * C + e * C * D + e * B * D + e * B * D + 4 * C * D + 4 * C, 4.0 * B * D * C),
         }
         names = [n for n, _ in sets[0].kernels()]
         reps = max(1, 1200 // S)

@@ -26,7 +26,7 @@ class HeadArgs(C.Structure):
         ("B", _i64), ("D", _i64), ("C", _i64),
         ("z", _p), ("ldz", _i64), ("loss_i", _p), ("loss_sum", _p), ("dz_bf16", _p), ("lddz", _i64),
         ("dx", _p), ("dx_dtype", _i32), ("lddx", _i64), ("dw", _p), ("lddw", _i64), ("db", _p),
-        ("argmax", _p), ("rank", _p), ("acc_counts", _p), ("ticket", _p), ("ws", _p), ("ws_bytes", _sz),
+        ("argmax", _p), ("rank", _p), ("acc_counts", _p), ("scratch", _p), ("ws", _p), ("ws_bytes", _sz),
     ]
 
 
@@ -41,6 +41,7 @@ SIGNATURES = {
     "iif_weights_from_counts": (_i32, [_p, _i64, _i64, _i32, _f64, _p, _p, _p]),
     "iif_softmax_ce_fwd_bwd": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _f32, _i64, _i64, _p, _p, _p, _i64, _p, _i64,
                                       _p, _p, _p, _p, _p, _p]),
+    "iif_loss_scratch_bytes": (_sz, [_i64]),
     "iif_scaled_activation": (_i32, [_p, _i64, _p, _i32, _i64, _i64, _p, _i64, _p, _p, _p, _p]),
     "iif_sigmoid_bce_fwd_bwd": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _f32, _i64, _i64, _p, _i64, _p, _p, _p, _i64,
                                        _p, _i64, _p, _p]),
@@ -52,6 +53,8 @@ SIGNATURES = {
     "iif_linear_bwd_dx_f32": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "iif_linear_bwd_dw_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _p, _sz, _p]),
     "iif_linear_bwd_dw_f32": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _p]),
+    "iif_linear_bwd_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _i64, _i64, _p,
+                                   _sz, _p]),
     "iif_gemm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "iif_head_fwd_bwd_bf16": (_i32, [C.POINTER(HeadArgs), _p]),
 }

@@ -21,7 +21,7 @@ extern "C" const char* iif_error_string(int code) {
   }
 }
 
-// fc_cls -> fused IIF softmax-CE fwd+bwd -> db, dX, dW on one stream (4-5 launches).
+// fc_cls -> fused IIF softmax-CE fwd+bwd -> {dX, dW, db} on one stream: 3 launches.
 extern "C" int iif_head_fwd_bwd_bf16(const iif_head_args* h, void* stream) {
   if (!h || !h->x || !h->w || !h->label || !h->z || !h->dz_bf16 || !h->dw) return IIF_EINVAL;
   if (h->lddz % 8 != 0) return IIF_EALIGN;
@@ -30,17 +30,8 @@ extern "C" int iif_head_fwd_bwd_bf16(const iif_head_args* h, void* stream) {
   if (rc) return rc;
   rc = iif_softmax_ce_fwd_bwd(h->z, h->ldz, h->iif, h->label, h->class_weight, h->sample_weight, h->ignore_index,
                               h->scale, h->B, h->C, h->loss_i, h->loss_sum, nullptr, 0, h->dz_bf16, h->lddz, nullptr,
-                              h->argmax, h->rank, h->acc_counts, h->ticket, stream);
+                              h->argmax, h->rank, h->acc_counts, h->scratch, stream);
   if (rc) return rc;
-  if (h->db) {
-    rc = iif_colsum(h->dz_bf16, IIF_DTYPE_BF16, h->lddz, nullptr, h->B, h->C, h->db, stream);
-    if (rc) return rc;
-  }
-  if (h->dx) {
-    rc = iif_linear_bwd_dx_bf16(h->dz_bf16, h->lddz, h->w, h->ldw, nullptr, h->dx, h->dx_dtype, h->lddx, h->B, h->D,
-                                h->C, h->ws, h->ws_bytes, stream);
-    if (rc) return rc;
-  }
-  return iif_linear_bwd_dw_bf16(h->dz_bf16, h->lddz, h->x, h->ldx, nullptr, h->dw, h->lddw, h->B, h->D, h->C, h->ws,
-                                h->ws_bytes, stream);
+  return iif_linear_bwd_bf16(h->dz_bf16, h->lddz, h->x, h->ldx, h->w, h->ldw, nullptr, h->dx, h->dx_dtype, h->lddx, h->dw,
+                             h->lddw, h->db, h->B, h->D, h->C, h->ws, h->ws_bytes, stream);
 }

@@ -1,6 +1,6 @@
 // (a)/(c) fc_cls GEMMs on the 5th-generation tensor cores: tcgen05.mma with the accumulator in
 // TMEM, operands staged in shared memory by TMA through an mbarrier ring, one elected thread
-// issuing the MMAs, a 4-warp epilogue reading TMEM with tcgen05.ld.
+// issuing the MMAs, a 4-warp TMEM drain and a block-wide coalesced epilogue.
 //
 //   OUT[M,N] = alpha * A[M,K] . B[N,K]^T (+ bias[n]),  out2 = OUT * col_scale[n]
 //
@@ -11,13 +11,30 @@
 //   dW  (a10): A = dZ[B,C] MN-major (m = c)  B = X[B,D] MN-major (n = d)  dW = dZ^T X
 // so no transposed copy of W, X or dZ is ever written to HBM.
 //
-// Tile: 128 x 128 x 64 per CTA, 6-stage ring (32 KB / stage), 128-byte swizzle.  The head shapes
-// are small (ImageNet-LT: 256x1000x2048), so K is split across CTAs to fill the 148 SMs; partial
-// tiles go through an L2-resident fp32 workspace and the LAST CTA of a tile (ticket) sums them in
-// split order -- deterministic, no float atomics.
+// One launch runs a GROUP of up to two problems (dX and dW share a launch: they depend on the same
+// dZ and together fill the 148 SMs); blockIdx.x -> (problem, tile, K split).
+//
+// Tile: 128 x 128 x 64 per CTA, 128-byte swizzle, ring of `stages` 32 KB stages.  The head shapes
+// are small (ImageNet-LT: 256 x 1000 x 2048), so K is split across the CTAs of a thread-block
+// CLUSTER (cluster size = number of K splits, <= 8): every CTA parks its fp32 partial tile in an
+// L2-resident workspace, the cluster barrier (release/acquire) orders the exchange, and then EVERY
+// CTA of the cluster reduces 1/splits of the tile's rows in split order -- a parallel,
+// deterministic reduction with no float atomics, no spin waits and no serial tail.
+//
+// Epilogue: the 4 drain warps move TMEM -> registers -> a padded staging tile in (recycled) stage
+// memory; after one block barrier all 256 threads write 512-byte row segments (one warp = one row of
+// the tile), so partials, fp32 / bf16 outputs and the IIF-scaled second output are fully coalesced.
+//
+// Bias gradient on the tensor cores: in the dW product the CTAs of the first tile column issue one
+// extra N=16 MMA per k-step against a constant tile of ones, so db[c] = sum_b dZ[b,c] * 1 falls out
+// of the same operand stream into 16 spare TMEM columns -- no column-sum kernel, no extra HBM read.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (warp w may only touch TMEM lanes 32*(w%4) .. +31).
+// warp 3 = ones tile, warps 4..7 = TMEM drain (warp w may only touch TMEM lanes 32*(w%4) .. +31).
+//
+// Every kernel begins with griddepcontrol.launch_dependents / .wait (programmatic dependent
+// launch): the prologue (barrier init, TMEM alloc, tensor-map prefetch) overlaps the tail of the
+// previous kernel of the step.
 #include <cuda.h>
 
 #include <mutex>
@@ -30,119 +47,128 @@ namespace iif {
 
 constexpr int TILE_M = 128;
 constexpr int TILE_K = 64;            // 64 bf16 = 128 bytes = one swizzle row
-constexpr int STAGES = 6;
+constexpr int BN = 128;
 constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * TILE_K * 2;      // 16 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int LDS = BN + 4;           // staging tile row pitch (floats): conflict-free float4 rows
+constexpr int MAX_STAGES = 6;
+constexpr int MAX_SPLITS = 8;         // portable cluster size
+constexpr int ONES_BYTES = 2048;      // 16 rows x 128 B of bf16 1.0 (K-major B operand of the db MMA)
+constexpr int TMEM_COLS = 256;        // BN accumulator columns + 16 for db (power of two)
 
-struct TcArgs {
+struct TcProblem {
   int M, N, K;
-  int kb_total, kb_per_split, splits;
-  const float* alpha; const float* bias; const float* col_scale;
-  void* out; int out_bf16; int64_t ldo; int out_vec;
-  float* out2; int64_t ldo2; int out2_vec;
-  float* partial; int* tickets;
+  int tiles_m, tiles_n, kb_total, kb_per_split, splits;
+  int a_mn, b_mn;
+  const float* alpha; const float* bias; const float* col_scale; int bias_vec;
+  void* out; int out_bf16; int out_vec; int64_t ldo;
+  float* out2; int out2_vec; int64_t ldo2;
+  float* partial;                                   // [tiles][splits][TILE_M][BN] fp32
+  float* db_out; float* db_partial;                 // dW only: db[m] (and [tiles_m][splits][TILE_M] partials)
 };
 
-template <int BN>
-struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = BN * TILE_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+struct TcGroup {
+  int nprob, stages, cluster;
+  int cta_begin[3];
+  TcProblem p[2];
 };
 
-template <int BN, bool OUT2>
-__device__ __forceinline__ void epilogue_store(const TcArgs& a, const float (&acc)[32], int m, int n_base, float alpha) {
-  // one thread = one output row, 32 consecutive columns starting at n_base
-  if (m >= a.M) return;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int n = n_base + j;
-    v[j] = acc[j] * alpha + ((a.bias && n < a.N) ? __ldg(a.bias + n) : 0.f);
-  }
-  const bool full = n_base + 32 <= a.N;
-  if (a.out) {
-    if (a.out_bf16) {
-      uint16_t* o = reinterpret_cast<uint16_t*>(a.out) + (int64_t)m * a.ldo + n_base;
-      if (full && a.out_vec) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 q = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                               pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-          *reinterpret_cast<uint4*>(o + j) = q;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (n_base + j < a.N) o[j] = bf16_bits(v[j]);
-      }
+__host__ __device__ inline int smem_bytes_for(int stages) { return stages * STAGE_BYTES + ONES_BYTES + 256 + 1024; }
+
+__device__ __forceinline__ void emit4(const TcProblem& P, int m, int n, float4 v, float alpha) {
+  // one thread = 4 consecutive columns of one output row
+  if (m >= P.M || n >= P.N) return;
+  float r[4] = {v.x * alpha, v.y * alpha, v.z * alpha, v.w * alpha};
+  const bool full = n + 4 <= P.N;
+  if (P.bias) {
+    if (full && P.bias_vec) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n));
+      r[0] += b.x; r[1] += b.y; r[2] += b.z; r[3] += b.w;
     } else {
-      float* o = reinterpret_cast<float*>(a.out) + (int64_t)m * a.ldo + n_base;
-      if (full && a.out_vec) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (n_base + j < a.N) o[j] = v[j];
-      }
+      for (int j = 0; j < 4; ++j) if (n + j < P.N) r[j] += __ldg(P.bias + n + j);
     }
   }
-  if constexpr (OUT2) {
-    if (a.out2) {
-      float* o = a.out2 + (int64_t)m * a.ldo2 + n_base;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n_base + j;
-        v[j] *= (n < a.N) ? __ldg(a.col_scale + n) : 0.f;
-      }
-      if (full && a.out2_vec) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (n_base + j < a.N) o[j] = v[j];
-      }
+  if (P.out) {
+    if (P.out_bf16) {
+      uint16_t* o = reinterpret_cast<uint16_t*>(P.out) + (int64_t)m * P.ldo + n;
+      if (full && P.out_vec) stg_stream2(o, pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
+      else for (int j = 0; j < 4; ++j) if (n + j < P.N) o[j] = bf16_bits(r[j]);
+    } else {
+      float* o = reinterpret_cast<float*>(P.out) + (int64_t)m * P.ldo + n;
+      if (full && P.out_vec) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
+      else for (int j = 0; j < 4; ++j) if (n + j < P.N) o[j] = r[j];
     }
+  }
+  if (P.out2) {
+    float* o = P.out2 + (int64_t)m * P.ldo2 + n;
+    for (int j = 0; j < 4; ++j) r[j] *= (n + j < P.N) ? __ldg(P.col_scale + n + j) : 0.f;
+    if (full && P.out2_vec) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
+    else for (int j = 0; j < 4; ++j) if (n + j < P.N) o[j] = r[j];
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-  using L = SmemLayout<BN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ TcGroup g) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int stages = g.stages;
+  const uint32_t ones_base = smem_base + stages * STAGE_BYTES;      // 1024-byte aligned
+  const uint32_t bar_base = ones_base + ONES_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
-  const uint32_t flag_slot = tmem_slot + 4;
-  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
-  volatile uint32_t* flag_p = reinterpret_cast<volatile uint32_t*>(smem_raw + (flag_slot - ptx::smem_u32(smem_raw)));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
+  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TILE_M, split = blockIdx.z;
-  const int kb_begin = split * a.kb_per_split;
-  const int kb_end = min(a.kb_total, kb_begin + a.kb_per_split);
+  const int pi = (g.nprob > 1 && (int)blockIdx.x >= g.cta_begin[1]) ? 1 : 0;
+  const TcProblem& P = g.p[pi];
+  const CUtensorMap* tmA = pi ? &tmA1 : &tmA0;
+  const CUtensorMap* tmB = pi ? &tmB1 : &tmB0;
+  const int local = (int)blockIdx.x - g.cta_begin[pi];
+  const int split = local % P.splits;
+  const int tile = local / P.splits;
+  const bool has_work = tile < P.tiles_m * P.tiles_n;
+  if (!has_work) {                       // padding CTA of a cluster: only keep the barrier balanced
+    if (P.splits > 1) ptx::cluster_sync();
+    return;
+  }
+  const int n0 = (tile % P.tiles_n) * BN, m0 = (tile / P.tiles_n) * TILE_M;
+  const int kb_begin = split * P.kb_per_split;
+  const int kb_end = min(P.kb_total, kb_begin + P.kb_per_split);
+  const bool do_db = P.db_out != nullptr && n0 == 0;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tmA);
-    ptx::prefetch_tensormap(&tmB);
+    ptx::prefetch_tensormap(tmA);
+    ptx::prefetch_tensormap(tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, BN);
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish();
+  }
+  if (warp == 3 && do_db) {                // constant B operand of the bias-gradient MMA
+    uint4* o = reinterpret_cast<uint4*>(smem_gen + (ones_base - smem_base));
+    const uint4 one = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    for (int i = lane; i < ONES_BYTES / 16; i += 32) o[i] = one;
+    ptx::fence_proxy_async();              // generic-proxy writes -> visible to the tensor core (async proxy)
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
+
+  ptx::griddep_launch_dependents();      // the next kernel may start its own prologue now
+  ptx::griddep_wait();                   // ... and ours ends here: the producer kernel's data is visible
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -150,111 +176,126 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
         const int k0 = kb * TILE_K;
-        if constexpr (A_MN) {
+        if (P.a_mn) {
 #pragma unroll
-          for (int j = 0; j < TILE_M / 64; ++j) ptx::tma_load_2d(sa + j * 8192, &tmA, full_bar(stage), m0 + 64 * j, k0);
+          for (int j = 0; j < TILE_M / 64; ++j) ptx::tma_load_2d(sa + j * 8192, tmA, full_bar(stage), m0 + 64 * j, k0);
         } else {
-          ptx::tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);
+          ptx::tma_load_2d(sa, tmA, full_bar(stage), k0, m0);
         }
-        if constexpr (B_MN) {
+        if (P.b_mn) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, &tmB, full_bar(stage), n0 + 64 * j, k0);
+          for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, tmB, full_bar(stage), n0 + 64 * j, k0);
         } else {
-          ptx::tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);
+          ptx::tma_load_2d(sb, tmB, full_bar(stage), k0, n0);
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN, A_MN, B_MN);
+      const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN, P.a_mn != 0, P.b_mn != 0);
+      const uint32_t idesc_db = ptx::make_idesc_bf16(TILE_M, 16, P.a_mn != 0, false);
+      // K-major: 16 bf16 = 32 bytes along the swizzle row; 8-row groups 1024 B apart (SBO).
+      // MN-major: 16 k-rows = 2048 bytes; 8-row groups 1024 B apart (SBO); 64-wide MN atoms 8192 B apart (LBO).
+      const uint32_t a_step = P.a_mn ? 2048u : 32u, a_lbo = P.a_mn ? 8192u : 16u;
+      const uint32_t b_step = P.b_mn ? 2048u : 32u, b_lbo = P.b_mn ? 8192u : 16u;
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
-        const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < TILE_K / 16; ++k) {
-          // K-major: 16 bf16 = 32 bytes along the swizzle row; 8-row groups 1024 B apart.
-          // MN-major: 16 k-rows = 2048 bytes; 8-row groups 1024 B apart (SBO); 64-wide MN atoms 8192 B apart (LBO).
-          const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
-                                   : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
-                                   : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-          ptx::umma_bf16(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          const uint64_t da = ptx::make_smem_desc_sw128(sa + k * a_step, a_lbo, 1024);
+          const uint64_t db = ptx::make_smem_desc_sw128(sb + k * b_step, b_lbo, 1024);
+          const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
+          ptx::umma_bf16(tmem_base, da, db, idesc, accum);
+          if (do_db)   // ones tile: every value equal, so the swizzle is immaterial
+            ptx::umma_bf16(tmem_base + BN, da, ptx::make_smem_desc_sw128(ones_base + k * 32, 16, 1024), idesc_db, accum);
         }
         ptx::umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
       ptx::umma_commit(tmem_full_bar);       // accumulator complete
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue: TMEM -> registers -> HBM =====================
+  } else if (warp < 4) {
+    // idle until the epilogue
+  } else {
+    // ===================== drain: TMEM -> registers -> staging tile =====================
     const int q = warp & 3;                  // TMEM lane quarter owned by this warp
     const int row = q * 32 + lane;           // row inside the tile
-    const int m = m0 + row;
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float alpha = a.alpha ? __ldg(a.alpha) : 1.f;
-    if (a.splits == 1) {
+    float* srow = reinterpret_cast<float*>(smem_gen) + row * LDS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(taddr + c0, r);
-        ptx::tmem_ld_wait();
-        float acc[32];
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(taddr + c0, r);
+      ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-        if (n0 + c0 < a.N) epilogue_store<BN, true>(a, acc, m, n0 + c0, alpha);
-      }
-    } else {
-      const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-      float* mine = a.partial + ((int64_t)tile * a.splits + split) * (TILE_M * BN) + row * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(taddr + c0, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          __stcg(reinterpret_cast<float4*>(mine + c0 + j),
-                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 128) *flag_p = (atomicAdd(a.tickets + tile, 1) == a.splits - 1) ? 1u : 0u;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*flag_p) {
-        __threadfence();
-        const float* base = a.partial + (int64_t)tile * a.splits * (TILE_M * BN) + row * BN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (n0 + c0 >= a.N) break;
-          float acc[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-          for (int s = 0; s < a.splits; ++s) {   // fixed split order: deterministic sum
-            const float* p = base + (int64_t)s * (TILE_M * BN) + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(p + j));
-              acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
-            }
-          }
-          epilogue_store<BN, true>(a, acc, m, n0 + c0, alpha);
-        }
-        if (threadIdx.x == 128) a.tickets[tile] = 0;  // self-resetting
-      }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(srow + c0 + j) =
+            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    }
+    if (do_db) {                             // db partial of this row: first of the 16 equal columns
+      const uint32_t v = ptx::tmem_ld1(taddr + BN);
+      ptx::tmem_ld_wait();
+      srow[BN] = __uint_as_float(v);
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, BN);
+  __syncthreads();                           // staging tile complete; TMEM no longer needed
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+
+  // ===================== block-wide coalesced epilogue =====================
+  const float* stg = reinterpret_cast<const float*>(smem_gen);
+  const float alpha = P.alpha ? __ldg(P.alpha) : 1.f;
+  constexpr int F4 = BN / 4;                 // float4 per tile row: one warp covers one row
+  if (P.splits == 1) {
+    for (int idx = threadIdx.x; idx < TILE_M * F4; idx += 256) {
+      const int row = idx / F4, c4 = idx % F4;
+      emit4(P, m0 + row, n0 + c4 * 4, *reinterpret_cast<const float4*>(stg + row * LDS + c4 * 4), alpha);
+    }
+    if (do_db && threadIdx.x < TILE_M && m0 + (int)threadIdx.x < P.M)
+      P.db_out[m0 + threadIdx.x] = stg[threadIdx.x * LDS + BN] * alpha;
+  } else {
+    float4* base = reinterpret_cast<float4*>(P.partial) + (int64_t)tile * P.splits * (TILE_M * F4);
+    float4* mine = base + (int64_t)split * (TILE_M * F4);
+    for (int idx = threadIdx.x; idx < TILE_M * F4; idx += 256) {
+      const int row = idx / F4, c4 = idx % F4;
+      __stcg(mine + idx, *reinterpret_cast<const float4*>(stg + row * LDS + c4 * 4));
+    }
+    float* dbp = do_db ? P.db_partial + (int64_t)(tile / P.tiles_n) * P.splits * TILE_M : nullptr;
+    if (do_db && threadIdx.x < TILE_M) __stcg(dbp + split * TILE_M + threadIdx.x, stg[threadIdx.x * LDS + BN]);
+    ptx::cluster_sync();                     // release our partial / acquire the other splits'
+    const int rps = (TILE_M + P.splits - 1) / P.splits;
+    const int r0 = split * rps, r1 = min(TILE_M, r0 + rps);
+    for (int idx = threadIdx.x; idx < (r1 - r0) * F4; idx += 256) {
+      const int row = r0 + idx / F4, c4 = idx % F4;
+      float4 t[MAX_SPLITS];
+#pragma unroll
+      for (int s = 0; s < MAX_SPLITS; ++s)
+        if (s < P.splits) t[s] = __ldcg(base + (int64_t)s * (TILE_M * F4) + row * F4 + c4);
+      float4 acc = t[0];
+#pragma unroll
+      for (int s = 1; s < MAX_SPLITS; ++s)   // fixed split order: deterministic sum
+        if (s < P.splits) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }
+      emit4(P, m0 + row, n0 + c4 * 4, acc, alpha);
+    }
+    if (do_db && (int)threadIdx.x < r1 - r0 && m0 + r0 + (int)threadIdx.x < P.M) {
+      float acc = 0.f;
+      for (int s = 0; s < P.splits; ++s) acc += __ldcg(dbp + s * TILE_M + r0 + threadIdx.x);
+      P.db_out[m0 + r0 + threadIdx.x] = acc * alpha;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -317,80 +358,184 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
   return IIF_OK;
 }
 
-struct Plan { int tiles_m, tiles_n, kb_total, kb_per_split, splits; size_t ws_bytes; };
+struct Plan {
+  int tiles_m, tiles_n, kb_total, kb_per_split, splits; size_t partial_bytes;
+  size_t db_bytes() const { return splits > 1 ? (size_t)tiles_m * splits * TILE_M * 4 : 0; }   // 512-byte multiples
+};
 
-static Plan make_plan(int64_t M, int64_t N, int64_t K) {
-  constexpr int BN = 128;
+// K splits: the cluster size.  Cost model in k-block units: every CTA pays ~3 blocks of prologue +
+// epilogue, a split tile ~1.5 more for the exchange; CTAs run in waves of 148.
+static Plan make_plan(int64_t M, int64_t N, int64_t K, int other_ctas = 0) {
   Plan p;
   p.tiles_m = (int)((M + TILE_M - 1) / TILE_M);
   p.tiles_n = (int)((N + BN - 1) / BN);
   p.kb_total = (int)((K + TILE_K - 1) / TILE_K);
   if (p.kb_total < 1) p.kb_total = 1;
-  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n;
-  int want = tiles > 0 ? (int)(kNumSMs / tiles) : 1;   // fill one wave of the 148 SMs
-  if (want < 1) want = 1;
-  if (want > p.kb_total) want = p.kb_total;
-  p.kb_per_split = (p.kb_total + want - 1) / want;
-  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  p.ws_bytes = p.splits > 1 ? 1024 + ((size_t)tiles * 4 + 255) / 256 * 256 + (size_t)tiles * p.splits * TILE_M * BN * 4 : 0;
+  const int tiles = p.tiles_m * p.tiles_n;
+  double best = 1e30;
+  int best_s = 1;
+  for (int s = 1; s <= MAX_SPLITS && s <= p.kb_total; ++s) {
+    const int per = (p.kb_total + s - 1) / s;
+    if ((p.kb_total + per - 1) / per != s) continue;            // s must be reachable exactly
+    const int ctas = tiles * s + other_ctas;
+    const int waves = (ctas + kNumSMs - 1) / kNumSMs;
+    const double cost = waves * (per + 3.0 + (s > 1 ? 1.5 : 0.0));
+    if (cost < best - 1e-9) { best = cost; best_s = s; }
+  }
+  p.splits = best_s;
+  p.kb_per_split = (p.kb_total + best_s - 1) / best_s;
+  p.partial_bytes = p.splits > 1 ? (size_t)tiles * p.splits * TILE_M * BN * 4 : 0;
   return p;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, const Plan& p, cudaStream_t st) {
+struct GemmDesc {
+  const void* A; int64_t lda; bool a_mn;
+  const void* Bm; int64_t ldb; bool b_mn;
+  int64_t M, N, K;
+  const float* alpha; const float* bias; const float* col_scale;
+  void* out; int out_bf16; int64_t ldo;
+  float* out2; int64_t ldo2;
+  float* db_out;
+};
+
+static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, float* db_partial, TcProblem* P, CUtensorMap* ma,
+                        CUtensorMap* mb) {
+  if (!aligned16(d.A) || !aligned16(d.Bm) || d.lda % 8 || d.ldb % 8) return IIF_EALIGN;
+  int rc;
+  // K-major: memory [MN rows, K cols]; MN-major: memory [K rows, MN cols]
+  rc = d.a_mn ? make_map(ma, d.A, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, 64)
+              : make_map(ma, d.A, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)d.lda, TILE_M);
+  if (rc) return rc;
+  rc = d.b_mn ? make_map(mb, d.Bm, (uint64_t)d.N, (uint64_t)d.K, (uint64_t)d.ldb, 64)
+              : make_map(mb, d.Bm, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)d.ldb, BN);
+  if (rc) return rc;
+  *P = TcProblem{};
+  P->M = (int)d.M; P->N = (int)d.N; P->K = (int)d.K;
+  P->tiles_m = p.tiles_m; P->tiles_n = p.tiles_n; P->kb_total = p.kb_total; P->kb_per_split = p.kb_per_split;
+  P->splits = p.splits; P->a_mn = d.a_mn; P->b_mn = d.b_mn;
+  P->alpha = d.alpha; P->bias = d.bias; P->col_scale = d.col_scale; P->bias_vec = d.bias && aligned16(d.bias);
+  P->out = d.out; P->out_bf16 = d.out_bf16; P->ldo = d.ldo;
+  P->out_vec = d.out && (d.out_bf16 ? ((reinterpret_cast<uintptr_t>(d.out) & 7u) == 0 && d.ldo % 4 == 0)
+                                    : (aligned16(d.out) && d.ldo % 4 == 0));
+  P->out2 = d.out2; P->ldo2 = d.ldo2; P->out2_vec = d.out2 && aligned16(d.out2) && d.ldo2 % 4 == 0;
+  P->partial = partial;
+  P->db_out = d.db_out; P->db_partial = db_partial;
+  return IIF_OK;
+}
+
+// Launch one or two problems in one grid.
+static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes, cudaStream_t st) {
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes_for(MAX_STAGES));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid(p.tiles_n, p.tiles_m, p.splits);
-  kern<<<grid, 256, SmemLayout<BN>::TOTAL, st>>>(ma, mb, a);
-  return launch_status();
-}
-
-// OUT[M,N] = alpha * A . B^T;  a_mn / b_mn: operand stored with M (N) contiguous.
-static int gemm_bf16(const void* A, int64_t lda, bool a_mn, const void* Bm, int64_t ldb, bool b_mn, int64_t M, int64_t N,
-                     int64_t K, const float* alpha, const float* bias, const float* col_scale, void* out, int out_bf16,
-                     int64_t ldo, float* out2, int64_t ldo2, void* ws, size_t ws_bytes, cudaStream_t st) {
-  constexpr int BN = 128;
-  if (M <= 0 || N <= 0) return IIF_OK;
-  if (!aligned16(A) || !aligned16(Bm) || lda % 8 || ldb % 8) return IIF_EALIGN;
-  const Plan p = make_plan(M, N, K);
-  if (p.splits > 1 && (!ws || ws_bytes < p.ws_bytes)) return IIF_EWORKSPACE;
-  CUtensorMap ma, mb;
-  int rc;
-  // K-major: memory [MN rows, K cols]; MN-major: memory [K rows, MN cols]
-  rc = a_mn ? make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64)
-            : make_map(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TILE_M);
-  if (rc) return rc;
-  rc = b_mn ? make_map(&mb, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64)
-            : make_map(&mb, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BN);
-  if (rc) return rc;
-  TcArgs a{};
-  a.M = (int)M; a.N = (int)N; a.K = (int)K;
-  a.kb_total = p.kb_total; a.kb_per_split = p.kb_per_split; a.splits = p.splits;
-  a.alpha = alpha; a.bias = bias; a.col_scale = col_scale;
-  a.out = out; a.out_bf16 = out_bf16; a.ldo = ldo;
-  a.out_vec = out && aligned16(out) && (out_bf16 ? ldo % 8 == 0 : ldo % 4 == 0);
-  a.out2 = out2; a.ldo2 = ldo2; a.out2_vec = out2 && aligned16(out2) && ldo2 % 4 == 0;
-  if (p.splits > 1) {
-    uint8_t* w = reinterpret_cast<uint8_t*>(ws);
-    const size_t tiles = (size_t)p.tiles_m * p.tiles_n;
-    a.tickets = reinterpret_cast<int*>(w);
-    size_t off = (tiles * 4 + 255) / 256 * 256;
-    off = (off + 1023) / 1024 * 1024;
-    a.partial = reinterpret_cast<float*>(w + off);
+  TcGroup g{};
+  CUtensorMap maps[4] = {};
+  Plan plans[2];
+  int tiles_total = 0;
+  for (int i = 0; i < nprob; ++i) {
+    if (!aligned16(d[i].A) || !aligned16(d[i].Bm)) return IIF_EALIGN;
+    tiles_total += (int)(((d[i].M + TILE_M - 1) / TILE_M) * ((d[i].N + BN - 1) / BN));
   }
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false>(ma, mb, a, p, st);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true>(ma, mb, a, p, st);
-  if (a_mn && b_mn) return launch_tc<BN, true, true>(ma, mb, a, p, st);
-  return launch_tc<BN, true, false>(ma, mb, a, p, st);
+  for (int i = 0; i < nprob; ++i) {
+    const int mine = (int)(((d[i].M + TILE_M - 1) / TILE_M) * ((d[i].N + BN - 1) / BN));
+    plans[i] = make_plan(d[i].M, d[i].N, d[i].K, nprob > 1 ? tiles_total - mine : 0);
+  }
+  int cluster = 1;
+  for (int i = 0; i < nprob; ++i) if (plans[i].splits > cluster) cluster = plans[i].splits;
+  // a problem's splits must divide the cluster size so that clusters never straddle tiles unevenly
+  for (int i = 0; i < nprob; ++i)
+    while (cluster % plans[i].splits) {       // fall back to the next smaller exact split count
+      int s = plans[i].splits - 1;
+      for (; s > 1; --s) {
+        const int per = (plans[i].kb_total + s - 1) / s;
+        if ((plans[i].kb_total + per - 1) / per == s && cluster % s == 0) break;
+      }
+      if (s < 1) s = 1;
+      plans[i].splits = s;
+      plans[i].kb_per_split = (plans[i].kb_total + s - 1) / s;
+      const int tiles = plans[i].tiles_m * plans[i].tiles_n;
+      plans[i].partial_bytes = s > 1 ? (size_t)tiles * s * TILE_M * BN * 4 : 0;
+    }
+  size_t need = 0;
+  for (int i = 0; i < nprob; ++i) need += plans[i].partial_bytes + (d[i].db_out ? plans[i].db_bytes() : 0);
+  if (need && (!ws || ws_bytes < need)) return IIF_EWORKSPACE;
+  int cta = 0;
+  size_t off = 0;
+  for (int i = 0; i < nprob; ++i) {
+    float* partial = plans[i].partial_bytes ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + off) : nullptr;
+    off += plans[i].partial_bytes;
+    float* dbp = nullptr;
+    if (d[i].db_out && plans[i].db_bytes()) {
+      dbp = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + off);
+      off += plans[i].db_bytes();
+    }
+    int rc = fill_problem(d[i], plans[i], partial, dbp, &g.p[i], &maps[2 * i], &maps[2 * i + 1]);
+    if (rc) return rc;
+    g.cta_begin[i] = cta;
+    int n = plans[i].tiles_m * plans[i].tiles_n * plans[i].splits;
+    n = (n + cluster - 1) / cluster * cluster;          // pad to whole clusters
+    cta += n;
+  }
+  g.cta_begin[nprob] = cta;
+  g.nprob = nprob;
+  g.cluster = cluster;
+  g.stages = MAX_STAGES;
+  if (nprob == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
+
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)cta);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem_bytes_for(g.stages);
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (cluster > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = (unsigned)cluster;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], g);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return (int)e;
+  return IIF_OK;
 }
 
 static bool bad_dims(int64_t B, int64_t D, int64_t C) {
   return B < 0 || D <= 0 || C <= 0 || B > INT32_MAX || D > INT32_MAX || C > INT32_MAX;
+}
+
+static GemmDesc desc_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* cs,
+                         float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B, int64_t D, int64_t C) {
+  GemmDesc d{};
+  d.A = x; d.lda = ldx; d.a_mn = false; d.Bm = w; d.ldb = ldw; d.b_mn = false; d.M = B; d.N = C; d.K = D;
+  d.bias = bias; d.col_scale = cs; d.out = z; d.out_bf16 = 0; d.ldo = ldz; d.out2 = zs; d.ldo2 = ldzs;
+  return d;
+}
+static GemmDesc desc_dx(const void* dz, int64_t lddz, const void* w, int64_t ldw, const float* alpha, void* dx,
+                        int dx_bf16, int64_t lddx, int64_t B, int64_t D, int64_t C) {
+  GemmDesc d{};
+  d.A = dz; d.lda = lddz; d.a_mn = false; d.Bm = w; d.ldb = ldw; d.b_mn = true; d.M = B; d.N = D; d.K = C;
+  d.alpha = alpha; d.out = dx; d.out_bf16 = dx_bf16; d.ldo = lddx;
+  return d;
+}
+static GemmDesc desc_dw(const void* dz, int64_t lddz, const void* x, int64_t ldx, const float* alpha, float* dw,
+                        int64_t lddw, int64_t B, int64_t D, int64_t C, float* db_out) {
+  GemmDesc d{};
+  d.A = dz; d.lda = lddz; d.a_mn = true; d.Bm = x; d.ldb = ldx; d.b_mn = true; d.M = C; d.N = D; d.K = B;
+  d.alpha = alpha; d.out = dw; d.out_bf16 = 0; d.ldo = lddw;
+  d.db_out = db_out;
+  return d;
 }
 
 }  // namespace iif
@@ -399,9 +544,20 @@ using namespace iif;
 
 extern "C" size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C) {
   if (B <= 0 || D <= 0 || C <= 0) return 0;
-  size_t m = make_plan(B, C, D).ws_bytes;
-  size_t t = make_plan(B, D, C).ws_bytes; if (t > m) m = t;
-  t = make_plan(C, D, B).ws_bytes; if (t > m) m = t;
+  // upper bound: any problem of the head with the largest split count
+  auto cap = [](int64_t M, int64_t N) {
+    return (size_t)((M + TILE_M - 1) / TILE_M) * (size_t)((N + BN - 1) / BN) * MAX_SPLITS * TILE_M * BN * 4;
+  };
+  auto need = [&](int64_t M, int64_t N, int64_t K, int other) {
+    const Plan p = make_plan(M, N, K, other);
+    return p.splits > 1 ? cap(M, N) / MAX_SPLITS * p.splits + p.db_bytes() : (size_t)0;
+  };
+  const int t_dx = (int)(((B + TILE_M - 1) / TILE_M) * ((D + BN - 1) / BN));
+  const int t_dw = (int)(((C + TILE_M - 1) / TILE_M) * ((D + BN - 1) / BN));
+  size_t m = need(B, C, D, 0);
+  size_t t = need(B, D, C, 0); if (t > m) m = t;
+  t = need(C, D, B, 0); if (t > m) m = t;
+  t = need(B, D, C, t_dw) + need(C, D, B, t_dx); if (t > m) m = t;
   return m;
 }
 
@@ -410,8 +566,9 @@ extern "C" int iif_linear_fwd_bf16(const void* x, int64_t ldx, const void* w, in
                                    int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream) {
   if (bad_dims(B, D, C) || !w || (B > 0 && !x) || (!z && !zs) || ldx < D || ldw < D) return IIF_EINVAL;
   if ((z && ldz < C) || (zs && (ldzs < C || !col_scale))) return IIF_EINVAL;
-  return gemm_bf16(x, ldx, false, w, ldw, false, B, C, D, nullptr, bias, col_scale, z, 0, ldz, zs, ldzs, ws, ws_bytes,
-                   (cudaStream_t)stream);
+  if (B == 0) return IIF_OK;
+  const GemmDesc d = desc_fwd(x, ldx, w, ldw, bias, col_scale, z, ldz, zs, ldzs, B, D, C);
+  return launch_group(&d, 1, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int iif_linear_bwd_dx_bf16(const void* dz, int64_t lddz, const void* w, int64_t ldw, const float* alpha_dev,
@@ -419,8 +576,9 @@ extern "C" int iif_linear_bwd_dx_bf16(const void* dz, int64_t lddz, const void* 
                                       size_t ws_bytes, void* stream) {
   if (bad_dims(B, D, C) || !w || !dx || (B > 0 && !dz) || lddz < C || ldw < D || lddx < D) return IIF_EINVAL;
   if (dx_dtype != IIF_DTYPE_F32 && dx_dtype != IIF_DTYPE_BF16) return IIF_EINVAL;
-  return gemm_bf16(dz, lddz, false, w, ldw, true, B, D, C, alpha_dev, nullptr, nullptr, dx, dx_dtype == IIF_DTYPE_BF16,
-                   lddx, nullptr, 0, ws, ws_bytes, (cudaStream_t)stream);
+  if (B == 0) return IIF_OK;
+  const GemmDesc d = desc_dx(dz, lddz, w, ldw, alpha_dev, dx, dx_dtype == IIF_DTYPE_BF16, lddx, B, D, C);
+  return launch_group(&d, 1, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int iif_linear_bwd_dw_bf16(const void* dz, int64_t lddz, const void* x, int64_t ldx, const float* alpha_dev,
@@ -431,6 +589,25 @@ extern "C" int iif_linear_bwd_dw_bf16(const void* dz, int64_t lddz, const void* 
     cudaError_t e = cudaMemset2DAsync(dw, lddw * 4, 0, D * 4, C, (cudaStream_t)stream);
     return e == cudaSuccess ? IIF_OK : (int)e;
   }
-  return gemm_bf16(dz, lddz, true, x, ldx, true, C, D, B, alpha_dev, nullptr, nullptr, dw, 0, lddw, nullptr, 0, ws,
-                   ws_bytes, (cudaStream_t)stream);
+  const GemmDesc d = desc_dw(dz, lddz, x, ldx, alpha_dev, dw, lddw, B, D, C, nullptr);
+  return launch_group(&d, 1, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
+                                   const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw,
+                                   int64_t lddw, float* db, int64_t B, int64_t D, int64_t C, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  if (bad_dims(B, D, C) || !dw || (B > 0 && (!dz || !x)) || lddz < C || ldx < D || lddw < D) return IIF_EINVAL;
+  if (dx && (!w || ldw < D || lddx < D || (dx_dtype != IIF_DTYPE_F32 && dx_dtype != IIF_DTYPE_BF16))) return IIF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {  // empty batch: the parameter gradients are exactly zero, dX is empty
+    cudaError_t e = cudaMemset2DAsync(dw, lddw * 4, 0, D * 4, C, st);
+    if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, C * 4, st);
+    return e == cudaSuccess ? IIF_OK : (int)e;
+  }
+  GemmDesc d[2];
+  int n = 0;
+  if (dx) d[n++] = desc_dx(dz, lddz, w, ldw, alpha_dev, dx, dx_dtype == IIF_DTYPE_BF16, lddx, B, D, C);
+  d[n++] = desc_dw(dz, lddz, x, ldx, alpha_dev, dw, lddw, B, D, C, db);
+  return launch_group(d, n, ws, ws_bytes, st);
 }

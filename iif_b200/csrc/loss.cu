@@ -9,6 +9,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace iif {
 
@@ -24,153 +25,181 @@ struct RowArgs {
   float* loss_i; float* loss_sum;
   float* dz32; int64_t lddz32;
   uint16_t* dz16; int64_t lddz16;
-  float* lse; int32_t* argmax; int32_t* rank; int32_t* acc_counts; int32_t* ticket;
+  float* lse; int32_t* argmax; int32_t* rank; int32_t* acc_counts; int32_t* scratch;
   float* out; int64_t ldo; int softmax; int on_scaled;
 };
 
-// ---- reductions over the TPR threads that own one row (TPR is a multiple of 32) -----------------
-template <int TPR>
-__device__ __forceinline__ void row_reduce_pass1(float& m, float& bv, int& bi, int& cnt, float* s_m,
-                                                 float* s_bv, int* s_bi, int* s_cnt) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  }
-  if constexpr (TPR > 32) {
-    constexpr int WPR = TPR / 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { s_m[warp] = m; s_bv[warp] = bv; s_bi[warp] = bi; s_cnt[warp] = cnt; }
-    __syncthreads();
-    const int w0 = (warp / WPR) * WPR;
-    m = s_m[w0]; bv = s_bv[w0]; bi = s_bi[w0]; cnt = s_cnt[w0];
-#pragma unroll 1
-    for (int w = 1; w < WPR; ++w) {
-      m = fmaxf(m, s_m[w0 + w]);
-      float ov = s_bv[w0 + w]; int oi = s_bi[w0 + w];
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      cnt += s_cnt[w0 + w];
-    }
-  }
-}
+// scratch layout: [0] ticket (zero on entry, reset on exit) | 16: double part[grid] | int c1[grid] | int c5[grid]
+__host__ __device__ inline size_t scratch_bytes_for(int64_t grid) { return 16 + (size_t)grid * 16; }
 
-template <int TPR>
-__device__ __forceinline__ float row_reduce_sum(float v, float* s_v) {
-  v = warp_sum(v);
-  if constexpr (TPR > 32) {
-    constexpr int WPR = TPR / 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) s_v[warp] = v;
-    __syncthreads();
-    const int w0 = (warp / WPR) * WPR;
-    v = s_v[w0];
-#pragma unroll 1
-    for (int w = 1; w < WPR; ++w) v += s_v[w0 + w];
-  }
-  return v;
-}
-
-// Deterministic tail executed by the last CTA to finish: fixed-order sum of loss_i and the top-k
-// hit counts.  `ticket` is self-resetting.
-__device__ __forceinline__ void last_block_reduce(const float* loss_i, const int32_t* rank, int64_t B,
-                                                  float* loss_sum, int32_t* acc_counts, int32_t* ticket) {
-  __shared__ int s_last;
-  __shared__ double s_acc[32];
-  __shared__ int s_c1[32], s_c5[32];
-  __threadfence();
+template <int THREADS>
+__device__ __forceinline__ double block_sum_d(double v, double* s) {   // fixed order: deterministic
+  v = warp_sum_d(v);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  double r = 0.0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) r += s[w];
+  __syncthreads();
+  return r;
+}
+template <int THREADS>
+__device__ __forceinline__ int block_sum_i(int v, int* s) {
+  v = warp_sum_i(v);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) r += s[w];
+  __syncthreads();
+  return r;
+}
+
+// Grid-wide tail: every CTA has published one partial (loss sum, top-1 / top-5 hits); the last CTA
+// to take a ticket adds them in index order.  Only thread 0 fences -- the dZ stores of the other
+// threads are ordered by the kernel boundary, not by this reduction.
+template <int THREADS>
+__device__ __forceinline__ void grid_tail(double part, int c1, int c5, float* loss_sum, int32_t* acc_counts,
+                                          int32_t* scratch) {
+  __shared__ int s_last;
+  __shared__ double s_d[THREADS / 32];
+  __shared__ int s_i[THREADS / 32];
+  double* g_part = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(scratch) + 16);
+  int* g_c1 = reinterpret_cast<int*>(g_part + gridDim.x);
+  int* g_c5 = g_c1 + gridDim.x;
+  if (threadIdx.x == 0) {
+    __stcg(g_part + blockIdx.x, part);
+    __stcg(g_c1 + blockIdx.x, c1);
+    __stcg(g_c5 + blockIdx.x, c5);
+    __threadfence();
+    s_last = (atomicAdd(scratch, 1) == (int)gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   double acc = 0.0;
-  int c1 = 0, c5 = 0;
-  for (int64_t i = threadIdx.x; i < B; i += blockDim.x) {
-    if (loss_sum) acc += (double)__ldcg(loss_i + i);
-    if (acc_counts) { int r = __ldcg(rank + i); c1 += (r < 1); c5 += (r < 5); }
+  int k1 = 0, k5 = 0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) {
+    acc += __ldcg(g_part + i); k1 += __ldcg(g_c1 + i); k5 += __ldcg(g_c5 + i);
   }
-  acc = warp_sum_d(acc); c1 = warp_sum_i(c1); c5 = warp_sum_i(c5);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-  if (lane == 0) { s_acc[warp] = acc; s_c1[warp] = c1; s_c5[warp] = c5; }
-  __syncthreads();
+  acc = block_sum_d<THREADS>(acc, s_d);
+  k1 = block_sum_i<THREADS>(k1, s_i);
+  k5 = block_sum_i<THREADS>(k5, s_i);
   if (threadIdx.x == 0) {
-    double a = 0.0; int k1 = 0, k5 = 0;
-    for (int w = 0; w < nw; ++w) { a += s_acc[w]; k1 += s_c1[w]; k5 += s_c5[w]; }
-    if (loss_sum) *loss_sum = (float)a;
+    if (loss_sum) *loss_sum = (float)acc;
     if (acc_counts) { acc_counts[0] = k1; acc_counts[1] = k5; }
-    *ticket = 0;
+    *scratch = 0;   // self-resetting ticket
   }
 }
 
 // MODE 0: softmax-CE forward + backward.  MODE 1: activation (softmax(z*iif) or z*iif).
+// TPR threads share one row (NE elements each); a CTA of max(TPR,256) threads holds 256/TPR rows.
+// Small batches use wide rows (TPR = C/4: one 128-bit load per thread, short dependency chains, every
+// SM busy); large batches use NE = 8 for more bytes in flight per SM.
 template <int TPR, int NE, bool VEC, int MODE>
 __global__ void __launch_bounds__(TPR > 256 ? TPR : 256)
 row_softmax_kernel(const RowArgs a) {
-  __shared__ float s_m[32], s_bv[32], s_sum[32];
-  __shared__ int s_bi[32], s_cnt[32];
+  constexpr int THREADS = TPR > 256 ? TPR : 256;
+  constexpr int WPR = TPR / 32;            // warps per row
+  constexpr int NW = THREADS / 32;
+  __shared__ float s_f[3][NW];
+  __shared__ int s_i[NW];
+  __shared__ float s_row_loss[THREADS / TPR];
+  __shared__ int s_row_rank[THREADS / TPR];
+  ptx::griddep_wait();
+  ptx::griddep_launch_dependents();
   const int t = threadIdx.x % TPR;
-  const int rpb = blockDim.x / TPR;
-  const int64_t row = (int64_t)blockIdx.x * rpb + threadIdx.x / TPR;
+  const int lrow = threadIdx.x / TPR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w0 = (warp / WPR) * WPR;      // first warp of this row
+  const int64_t row = (int64_t)blockIdx.x * (THREADS / TPR) + lrow;
   const bool active = row < a.B;
   const int C = a.C;
   const float* zr = a.z + (active ? row : 0) * a.ldz;
+  const bool want_rank = a.rank != nullptr, want_arg = a.argmax != nullptr;
 
   int64_t y = -1;
-  if (active && a.label) y = a.label[row];
+  if (active && a.label) y = __ldg(a.label + row);
   const bool y_in = active && y >= 0 && y < C;
   const bool y_ok = y_in && y != a.ignore_index;
-  const float zy = y_in ? zr[y] : 0.f;
-  const float sy = (y_in && a.iif) ? a.iif[y] : 1.f;
-  const float ref = a.on_scaled ? zy * sy : zy;
   const int yi = y_in ? (int)y : -1;
+  // label-dependent scalars: issued now, consumed after the reductions
+  const float sy = (y_in && a.iif) ? __ldg(a.iif + y) : 1.f;
+  float g = 0.f;
+  if (MODE == 0 && y_ok) {
+    g = a.scale;
+    if (a.cw) g *= __ldg(a.cw + y);
+    if (a.sw) g *= __ldg(a.sw + row);
+  }
 
-  float v[NE];
-  float m = -CUDART_INF_F, bv = -CUDART_INF_F;
-  int bi = 0x7fffffff, cnt = 0;
-
-  auto visit = [&](int e, int col, float z, float s) {
-    const float sc = z * s;
-    const float cmp = a.on_scaled ? sc : z;
-    if (cmp > bv) { bv = cmp; bi = col; }
-    cnt += (cmp > ref) || (cmp == ref && col < yi);
-    v[e] = sc;
-    m = fmaxf(m, sc);
-  };
-
+  float v[NE];                             // raw logits, later exp(scaled - max)
   if constexpr (VEC) {
 #pragma unroll
     for (int q = 0; q < NE / 4; ++q) {
       const int col = (q * TPR + t) * 4;
-      if (active && col < C) {
-        const float4 z4 = ldg_stream4(zr + col);
-        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (a.iif) s4 = __ldg(reinterpret_cast<const float4*>(a.iif + col));
-        visit(4 * q + 0, col + 0, z4.x, s4.x);
-        visit(4 * q + 1, col + 1, z4.y, s4.y);
-        visit(4 * q + 2, col + 2, z4.z, s4.z);
-        visit(4 * q + 3, col + 3, z4.w, s4.w);
-      } else {
-        v[4 * q] = v[4 * q + 1] = v[4 * q + 2] = v[4 * q + 3] = -CUDART_INF_F;
-      }
+      float4 z4 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+      if (active && col < C) z4 = ldg_stream4(zr + col);
+      v[4 * q] = z4.x; v[4 * q + 1] = z4.y; v[4 * q + 2] = z4.z; v[4 * q + 3] = z4.w;
     }
   } else {
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const int col = e * TPR + t;
-      if (active && col < C) visit(e, col, __ldg(zr + col), a.iif ? __ldg(a.iif + col) : 1.f);
-      else v[e] = -CUDART_INF_F;
+      v[e] = (active && col < C) ? __ldg(zr + col) : -CUDART_INF_F;
     }
   }
-  if (yi < 0) cnt = C;  // label outside [0,C): never inside any top-k
-  row_reduce_pass1<TPR>(m, bv, bi, cnt, s_m, s_bv, s_bi, s_cnt);
-  if (yi < 0) cnt = C;
+  auto col_of = [&](int e) { return VEC ? ((e >> 2) * TPR + t) * 4 + (e & 3) : e * TPR + t; };
+  auto scale_of = [&](int e) -> float {
+    const int col = col_of(e);
+    return (a.iif && col < C) ? __ldg(a.iif + col) : 1.f;
+  };
+
+  // ---- pass 1: row max of the scaled logits, arg max, the label's raw logit
+  float m = -CUDART_INF_F, bv = -CUDART_INF_F, zy = -CUDART_INF_F;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int col = col_of(e);
+    const bool in = active && col < C;
+    const float z = v[e];
+    const float sc = in ? z * scale_of(e) : -CUDART_INF_F;
+    m = fmaxf(m, sc);
+    if (want_arg) {
+      const float cmp = a.on_scaled ? sc : z;
+      if (in && cmp > bv) { bv = cmp; bi = col; }
+    }
+    if (in && col == yi) zy = z;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    zy = fmaxf(zy, __shfl_xor_sync(0xffffffffu, zy, o));
+    if (want_arg) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+  }
+  if constexpr (WPR > 1) {
+    if (lane == 0) { s_f[0][warp] = m; s_f[1][warp] = zy; s_f[2][warp] = bv; s_i[warp] = bi; }
+    __syncthreads();
+    m = s_f[0][w0]; zy = s_f[1][w0]; bv = s_f[2][w0]; bi = s_i[w0];
+#pragma unroll
+    for (int w = 1; w < WPR; ++w) {
+      m = fmaxf(m, s_f[0][w0 + w]);
+      zy = fmaxf(zy, s_f[1][w0 + w]);
+      const float ov = s_f[2][w0 + w]; const int oi = s_i[w0 + w];
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+  }
+  if (yi < 0) zy = 0.f;
 
   if (MODE == 1 && !a.softmax) {
     // out = z * iif  (cls/custom.py:38)
     float* o = a.out + (active ? row : 0) * a.ldo;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) v[e] *= scale_of(e);
     if constexpr (VEC) {
 #pragma unroll
       for (int q = 0; q < NE / 4; ++q) {
@@ -184,12 +213,43 @@ row_softmax_kernel(const RowArgs a) {
         if (active && col < C) o[col] = v[e];
       }
     }
-  } else {
-    const float mm = (m == -CUDART_INF_F) ? 0.f : m;
-    float sum = 0.f;
+  }
+
+  // ---- pass 2: exp-sum; rank of the label (needs the label's logit, now known)
+  const float mm = (m == -CUDART_INF_F) ? 0.f : m;
+  const float ref = a.on_scaled ? zy * sy : zy;
+  float sum = 0.f;
+  int cnt = 0;
+  const bool need_exp = !(MODE == 1 && !a.softmax);
 #pragma unroll
-    for (int e = 0; e < NE; ++e) { v[e] = expf(v[e] - mm); sum += v[e]; }
-    sum = row_reduce_sum<TPR>(sum, s_sum);
+  for (int e = 0; e < NE; ++e) {
+    const int col = col_of(e);
+    const bool in = active && col < C;
+    const float z = (MODE == 1 && !a.softmax) ? v[e] : v[e];   // activation mode already holds z*iif
+    const float sc = (MODE == 1 && !a.softmax) ? z : (in ? z * scale_of(e) : -CUDART_INF_F);
+    if (want_rank) {
+      const float cmp = (a.on_scaled || (MODE == 1 && !a.softmax)) ? sc : z;
+      cnt += in && ((cmp > ref) || (cmp == ref && col < yi));
+    }
+    if (need_exp) {
+      const float ex = in ? expf(sc - mm) : 0.f;
+      v[e] = ex;
+      sum += ex;
+    }
+  }
+  sum = warp_sum(sum);
+  if (want_rank) cnt = warp_sum_i(cnt);
+  if constexpr (WPR > 1) {
+    if (lane == 0) { s_f[0][warp] = sum; s_i[warp] = cnt; }
+    __syncthreads();
+    sum = s_f[0][w0]; cnt = s_i[w0];
+#pragma unroll
+    for (int w = 1; w < WPR; ++w) { sum += s_f[0][w0 + w]; cnt += s_i[w0 + w]; }
+  }
+  if (yi < 0) cnt = C;  // label outside [0,C): never inside any top-k
+
+  float my_loss = 0.f;
+  if (need_exp) {
     const float inv = 1.f / sum;
     if constexpr (MODE == 1) {
       float* o = a.out + (active ? row : 0) * a.ldo;
@@ -209,14 +269,9 @@ row_softmax_kernel(const RowArgs a) {
       }
     } else {
       const float lse = mm + logf(sum);
-      float g = 0.f;
-      if (y_ok) {
-        g = a.scale;
-        if (a.cw) g *= a.cw[y];
-        if (a.sw) g *= a.sw[row];
-      }
+      my_loss = y_ok ? g * (lse - zy * sy) : 0.f;
       if (active && t == 0) {
-        if (a.loss_i) a.loss_i[row] = y_ok ? g * (lse - zy * sy) : 0.f;
+        if (a.loss_i) a.loss_i[row] = my_loss;
         if (a.lse) a.lse[row] = lse;
       }
       if (a.dz32 || a.dz16) {
@@ -227,13 +282,11 @@ row_softmax_kernel(const RowArgs a) {
           for (int q = 0; q < NE / 4; ++q) {
             const int col = (q * TPR + t) * 4;
             if (active && col < C) {
-              float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (a.iif) s4 = __ldg(reinterpret_cast<const float4*>(a.iif + col));
               float4 d;
-              d.x = s4.x * g * (v[4 * q + 0] * inv - (col + 0 == yi ? 1.f : 0.f));
-              d.y = s4.y * g * (v[4 * q + 1] * inv - (col + 1 == yi ? 1.f : 0.f));
-              d.z = s4.z * g * (v[4 * q + 2] * inv - (col + 2 == yi ? 1.f : 0.f));
-              d.w = s4.w * g * (v[4 * q + 3] * inv - (col + 3 == yi ? 1.f : 0.f));
+              d.x = scale_of(4 * q + 0) * g * (v[4 * q + 0] * inv - (col + 0 == yi ? 1.f : 0.f));
+              d.y = scale_of(4 * q + 1) * g * (v[4 * q + 1] * inv - (col + 1 == yi ? 1.f : 0.f));
+              d.z = scale_of(4 * q + 2) * g * (v[4 * q + 2] * inv - (col + 2 == yi ? 1.f : 0.f));
+              d.w = scale_of(4 * q + 3) * g * (v[4 * q + 3] * inv - (col + 3 == yi ? 1.f : 0.f));
               if (!y_ok) d = make_float4(0.f, 0.f, 0.f, 0.f);  // ignored row: exact zeros even for inf weights
               if (d32) stg_stream4(d32 + col, d);
               if (d16) stg_stream2(d16 + col, pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
@@ -244,8 +297,7 @@ row_softmax_kernel(const RowArgs a) {
           for (int e = 0; e < NE; ++e) {
             const int col = e * TPR + t;
             if (active && col < C) {
-              const float s = a.iif ? __ldg(a.iif + col) : 1.f;
-              float d = s * g * (v[e] * inv - (col == yi ? 1.f : 0.f));
+              float d = scale_of(e) * g * (v[e] * inv - (col == yi ? 1.f : 0.f));
               if (!y_ok) d = 0.f;
               if (d32) d32[col] = d;
               if (d16) d16[col] = bf16_bits(d);
@@ -256,37 +308,71 @@ row_softmax_kernel(const RowArgs a) {
     }
   }
   if (active && t == 0) {
-    if (a.argmax) a.argmax[row] = bi;
-    if (a.rank) a.rank[row] = cnt;
+    if (want_arg) a.argmax[row] = bi;
+    if (want_rank) a.rank[row] = cnt;
   }
   if constexpr (MODE == 0) {
-    if (a.loss_sum || a.acc_counts) last_block_reduce(a.loss_i, a.rank, a.B, a.loss_sum, a.acc_counts, a.ticket);
+    if (a.loss_sum || a.acc_counts) {
+      // CTA partial in row order, then the grid tail
+      if (t == 0) { s_row_loss[lrow] = active ? my_loss : 0.f; s_row_rank[lrow] = active ? cnt : 0x7fffffff; }
+      __syncthreads();
+      double part = 0.0;
+      int c1 = 0, c5 = 0;
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < THREADS / TPR; ++r) {
+          part += (double)s_row_loss[r];
+          c1 += s_row_rank[r] < 1; c5 += s_row_rank[r] < 5;
+        }
+      }
+      grid_tail<THREADS>(part, c1, c5, a.loss_sum, a.acc_counts, a.scratch);
+    }
   }
 }
 
 template <int TPR, int NE, int MODE>
 static int launch_row(const RowArgs& a, bool vec, cudaStream_t st) {
-  // rows per CTA: as many as fit 256 threads, but never fewer CTAs than ~2 per SM
-  int rpb = TPR >= 256 ? 1 : 256 / TPR;
-  while (rpb > 1 && (a.B + rpb - 1) / rpb < 2 * kNumSMs) rpb >>= 1;
-  const unsigned grid = (unsigned)((a.B + rpb - 1) / rpb);
-  if (vec) row_softmax_kernel<TPR, NE, true, MODE><<<grid, TPR * rpb, 0, st>>>(a);
-  else row_softmax_kernel<TPR, NE, false, MODE><<<grid, TPR * rpb, 0, st>>>(a);
-  return launch_status();
+  constexpr int THREADS = TPR > 256 ? TPR : 256;
+  constexpr int RPB = THREADS / TPR;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((a.B + RPB - 1) / RPB));
+  cfg.blockDim = dim3(THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = vec ? cudaLaunchKernelEx(&cfg, row_softmax_kernel<TPR, NE, true, MODE>, a)
+                      : cudaLaunchKernelEx(&cfg, row_softmax_kernel<TPR, NE, false, MODE>, a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return e == cudaSuccess ? IIF_OK : (int)e;
+}
+
+// rows per CTA of the configuration dispatch_row would pick (for the scratch size)
+static int row_config(int64_t B, int C, int* tpr, int* ne) {
+  const bool big = B > 2048;                 // plenty of rows: favour bytes in flight over row width
+  if (C <= 128) { *tpr = 32; *ne = 4; }
+  else if (C <= 256) { if (big) { *tpr = 32; *ne = 8; } else { *tpr = 64; *ne = 4; } }
+  else if (C <= 512) { if (big) { *tpr = 64; *ne = 8; } else { *tpr = 128; *ne = 4; } }
+  else if (C <= 1024) { if (big) { *tpr = 128; *ne = 8; } else { *tpr = 256; *ne = 4; } }
+  else if (C <= 2048) { *tpr = 256; *ne = 8; }
+  else if (C <= 4096) { *tpr = 256; *ne = 16; }
+  else if (C <= 8192) { *tpr = 256; *ne = 32; }
+  else if (C <= 16384) { *tpr = 512; *ne = 32; }
+  else if (C <= 32768) { *tpr = 1024; *ne = 32; }
+  else return IIF_EUNSUPPORTED;
+  return IIF_OK;
 }
 
 template <int MODE>
 static int dispatch_row(const RowArgs& a, bool vec, cudaStream_t st) {
-  const int C = a.C;
-  if (C <= 128) return launch_row<32, 4, MODE>(a, vec, st);
-  if (C <= 256) return launch_row<32, 8, MODE>(a, vec, st);
-  if (C <= 512) return launch_row<32, 16, MODE>(a, vec, st);
-  if (C <= 1024) return launch_row<32, 32, MODE>(a, vec, st);
-  if (C <= 2048) return launch_row<128, 16, MODE>(a, vec, st);
-  if (C <= 4096) return launch_row<128, 32, MODE>(a, vec, st);
-  if (C <= 8192) return launch_row<256, 32, MODE>(a, vec, st);
-  if (C <= 16384) return launch_row<512, 32, MODE>(a, vec, st);
-  if (C <= 32768) return launch_row<1024, 32, MODE>(a, vec, st);
+  int tpr, ne;
+  if (int rc = row_config(a.B, a.C, &tpr, &ne)) return rc;
+#define IIF_ROW(T, N) if (tpr == T && ne == N) return launch_row<T, N, MODE>(a, vec, st)
+  IIF_ROW(32, 4); IIF_ROW(32, 8); IIF_ROW(64, 4); IIF_ROW(64, 8); IIF_ROW(128, 4); IIF_ROW(128, 8);
+  IIF_ROW(256, 4); IIF_ROW(256, 8); IIF_ROW(256, 16); IIF_ROW(256, 32); IIF_ROW(512, 32); IIF_ROW(1024, 32);
+#undef IIF_ROW
   return IIF_EUNSUPPORTED;
 }
 
@@ -298,7 +384,7 @@ struct BceArgs {
   const float* pw; const float* colw; const float* sw;
   int64_t ignore_index; float scale; int64_t B; int C;
   float* loss_elem; int64_t ldl; float* loss_i; float* loss_sum;
-  float* dz32; int64_t lddz32; uint16_t* dz16; int64_t lddz16; int32_t* ticket;
+  float* dz32; int64_t lddz32; uint16_t* dz16; int64_t lddz16; int32_t* scratch;
 };
 
 __device__ __forceinline__ void bce_elem(float z, bool t, float pw, float wgt, float& loss, float& d) {
@@ -314,7 +400,9 @@ __device__ __forceinline__ void bce_elem(float z, bool t, float pw, float wgt, f
 template <bool VEC>
 __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
   constexpr int TPR = 128;
-  __shared__ float s_sum[32];
+  __shared__ float s_sum[8];
+  ptx::griddep_wait();
+  ptx::griddep_launch_dependents();
   const int t = threadIdx.x % TPR;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x / TPR) + threadIdx.x / TPR;
   const bool active = row < a.B;
@@ -358,9 +446,22 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
       }
     }
   }
-  acc = row_reduce_sum<TPR>(acc, s_sum);
+  acc = warp_sum(acc);                      // TPR = 128: 4 warps per row, 2 rows per CTA
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_sum[warp] = acc;
+  __syncthreads();
+  const int w0 = (warp / 4) * 4;
+  acc = (s_sum[w0] + s_sum[w0 + 1]) + (s_sum[w0 + 2] + s_sum[w0 + 3]);
   if (active && t == 0 && a.loss_i) a.loss_i[row] = acc;
-  if (a.loss_sum) last_block_reduce(a.loss_i, nullptr, a.B, a.loss_sum, nullptr, a.ticket);
+  if (a.loss_sum) {
+    double part = 0.0;
+    if (threadIdx.x == 0) {
+      part = (double)((s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]));
+      const int64_t row1 = (int64_t)blockIdx.x * 2 + 1;
+      if (row1 < a.B) part += (double)((s_sum[4] + s_sum[5]) + (s_sum[6] + s_sum[7]));
+    }
+    grid_tail<256>(part, 0, 0, a.loss_sum, nullptr, a.scratch);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,15 +520,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ dz
 
 using namespace iif;
 
+extern "C" size_t iif_loss_scratch_bytes(int64_t B) { return scratch_bytes_for(B > 0 ? B : 1); }
+
 extern "C" int iif_softmax_ce_fwd_bwd(const float* z, int64_t ldz, const float* iifv, const int64_t* label,
                                       const float* class_weight, const float* sample_weight, int64_t ignore_index,
                                       float scale, int64_t B, int64_t C, float* loss_i, float* loss_sum,
                                       float* dz_f32, int64_t lddz_f32, void* dz_bf16, int64_t lddz_bf16, float* lse,
-                                      int32_t* argmax, int32_t* rank, int32_t* acc_counts, int32_t* ticket,
+                                      int32_t* argmax, int32_t* rank, int32_t* acc_counts, int32_t* scratch,
                                       void* stream) {
   if (B < 0 || C <= 0 || (B > 0 && (!z || !label)) || ldz < C) return IIF_EINVAL;
   if ((dz_f32 && lddz_f32 < C) || (dz_bf16 && lddz_bf16 < C)) return IIF_EINVAL;
-  if ((loss_sum && !loss_i) || (acc_counts && !rank) || ((loss_sum || acc_counts) && !ticket)) return IIF_EINVAL;
+  if ((acc_counts && !rank) || ((loss_sum || acc_counts) && !scratch)) return IIF_EINVAL;
   if (C > 32768) return IIF_EUNSUPPORTED;
   if (B == 0) return IIF_OK;
   RowArgs a{};
@@ -435,7 +538,7 @@ extern "C" int iif_softmax_ce_fwd_bwd(const float* z, int64_t ldz, const float* 
   a.ignore_index = ignore_index; a.scale = scale; a.B = B; a.C = (int)C;
   a.loss_i = loss_i; a.loss_sum = loss_sum; a.dz32 = dz_f32; a.lddz32 = lddz_f32;
   a.dz16 = reinterpret_cast<uint16_t*>(dz_bf16); a.lddz16 = lddz_bf16; a.lse = lse; a.argmax = argmax; a.rank = rank;
-  a.acc_counts = acc_counts; a.ticket = ticket; a.on_scaled = 0;
+  a.acc_counts = acc_counts; a.scratch = scratch; a.on_scaled = 0;
   const bool vec = (C % 4 == 0) && (ldz % 4 == 0) && aligned16(z) && (!iifv || aligned16(iifv)) &&
                    (!dz_f32 || (aligned16(dz_f32) && lddz_f32 % 4 == 0)) &&
                    (!dz_bf16 || ((reinterpret_cast<uintptr_t>(dz_bf16) & 7u) == 0 && lddz_bf16 % 4 == 0));
@@ -461,17 +564,17 @@ extern "C" int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_
                                        const float* col_weight, const float* sample_weight, int64_t ignore_index,
                                        float scale, int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
                                        float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
-                                       int64_t lddz_bf16, int32_t* ticket, void* stream) {
+                                       int64_t lddz_bf16, int32_t* scratch, void* stream) {
   if (B < 0 || C <= 0 || (B > 0 && (!z || !label)) || ldz < C) return IIF_EINVAL;
   if ((dz_f32 && lddz_f32 < C) || (dz_bf16 && lddz_bf16 < C) || (loss_elem && ldl < C)) return IIF_EINVAL;
-  if (loss_sum && (!loss_i || !ticket)) return IIF_EINVAL;
+  if (loss_sum && !scratch) return IIF_EINVAL;
   if (C > (1 << 30)) return IIF_EUNSUPPORTED;
   if (B == 0) return IIF_OK;
   BceArgs a{};
   a.z = z; a.ldz = ldz; a.label = label; a.pw = pos_weight; a.colw = col_weight; a.sw = sample_weight;
   a.ignore_index = ignore_index; a.scale = scale; a.B = B; a.C = (int)C; a.loss_elem = loss_elem; a.ldl = ldl;
   a.loss_i = loss_i; a.loss_sum = loss_sum; a.dz32 = dz_f32; a.lddz32 = lddz_f32;
-  a.dz16 = reinterpret_cast<uint16_t*>(dz_bf16); a.lddz16 = lddz_bf16; a.ticket = ticket;
+  a.dz16 = reinterpret_cast<uint16_t*>(dz_bf16); a.lddz16 = lddz_bf16; a.scratch = scratch;
   const bool vec = (C % 4 == 0) && (ldz % 4 == 0) && aligned16(z) && (!pos_weight || aligned16(pos_weight)) &&
                    (!col_weight || aligned16(col_weight)) && (!loss_elem || (aligned16(loss_elem) && ldl % 4 == 0)) &&
                    (!dz_f32 || (aligned16(dz_f32) && lddz_f32 % 4 == 0)) &&

@@ -97,6 +97,16 @@ class _Linear(torch.autograd.Function):
         gz2 = _f32(gz.reshape(-1, gz.shape[-1]))
         dz = ops.scale_rows(gz2, None, bf16=True, pad_ld=True) if ctx.bf16 else gz2
         dx = dw = db = None
+        if ctx.bf16 and gz2.shape[0] > 0:
+            dx, dw, _ = ops.linear_bwd(dz, xo, wo, need_dx=ctx.needs_input_grad[0], need_db=False,
+                                       dx_bf16=(ctx.x_dtype == torch.bfloat16))
+            if dx is not None:
+                dx = dx.to(ctx.x_dtype).reshape(ctx.x_shape)
+            if not ctx.needs_input_grad[1]:
+                dw = None
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = ops.colsum(gz2)          # fp32 upstream gradient: exact bias gradient
+            return dx, dw, db, None, None
         if ctx.needs_input_grad[0]:
             dx = ops.linear_bwd_dx(dz, wo, out_bf16=(ctx.x_dtype == torch.bfloat16 and ctx.bf16))
             dx = dx.to(ctx.x_dtype).reshape(ctx.x_shape)
@@ -115,7 +125,7 @@ class _IIFHeadLoss(torch.autograd.Function):
     """fc_cls -> IIF softmax-CE in one autograd node (bf16 GEMM operands, fp32 accumulate / logits).
 
     forward : Z = X W^T + b (tcgen05), fused loss kernel emitting loss and bf16 dZ (never fp32 dZ in HBM)
-    backward: db = colsum(dZ), dX = g dZ W, dW = g dZ^T X with the upstream scalar g read on device
+    backward: dX = g dZ W, dW = g dZ^T X, db = g sum_i dZ_i in ONE grouped tcgen05 launch, the upstream scalar g read on device
     Returns (loss, raw logits Z); Z is non-differentiable (training accuracy is taken on raw logits,
     classification/train.py:81, mmdet iif_loss.py:103)."""
 
@@ -139,14 +149,20 @@ class _IIFHeadLoss(torch.autograd.Function):
     def backward(ctx, g, _gz):
         xo, wo, dzp = ctx.saved_tensors
         dz = dzp[:, :ctx.C]
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = ops.linear_bwd_dx(dz, wo, alpha=g, out_bf16=(ctx.x_dtype == torch.bfloat16))
+        if dz.shape[0] == 0:
+            return (
+                torch.zeros(ctx.x_shape, dtype=ctx.x_dtype, device=dz.device) if ctx.needs_input_grad[0] else None,
+                torch.zeros(wo.shape, dtype=torch.float32, device=dz.device) if ctx.needs_input_grad[1] else None,
+                torch.zeros(wo.shape[0], dtype=torch.float32, device=dz.device)
+                if (ctx.has_bias and ctx.needs_input_grad[2]) else None, None, None, None, None, None, None, None)
+        # dX, dW and db in one launch; the upstream scalar g is read on the device (no host sync)
+        dx, dw, db = ops.linear_bwd(dz, xo, wo, alpha=g, need_dx=ctx.needs_input_grad[0],
+                                    need_db=ctx.has_bias and ctx.needs_input_grad[2],
+                                    dx_bf16=(ctx.x_dtype == torch.bfloat16))
+        if dx is not None:
             dx = dx.to(ctx.x_dtype).reshape(ctx.x_shape)
-        if ctx.needs_input_grad[1]:
-            dw = ops.linear_bwd_dw(dz, xo, alpha=g)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(dz, alpha=g)
+        if not ctx.needs_input_grad[1]:
+            dw = None
         return dx, dw, db, None, None, None, None, None, None, None
 
 

@@ -12,8 +12,8 @@ import torch
 
 from . import _lib
 
-_WS = {}      # (device index, stream, bytes) -> zeroed workspace
-_TICKET = {}  # (device index, stream) -> zeroed int32[1]
+_WS = {}       # (device index, stream) -> GEMM workspace
+_SCRATCH = {}  # (device index, stream) -> zeroed loss scratch
 
 
 def _cuda(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
@@ -60,12 +60,14 @@ def _stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def ticket(device) -> torch.Tensor:
+def loss_scratch(device, B: int) -> torch.Tensor:
+    """Zeroed scratch of the fused loss kernels (ticket + per-CTA partials), one per (device, stream)."""
+    n = int(_lib.load().iif_loss_scratch_bytes(int(B)))
     key = (torch.device(device).index or 0, torch.cuda.current_stream(device).cuda_stream)
-    t = _TICKET.get(key)
-    if t is None:
-        t = torch.zeros(1, dtype=torch.int32, device=device)
-        _TICKET[key] = t
+    t = _SCRATCH.get(key)
+    if t is None or t.numel() * 4 < n:
+        t = torch.zeros((n + 3) // 4, dtype=torch.int32, device=device)
+        _SCRATCH[key] = t
     return t
 
 
@@ -76,7 +78,7 @@ def gemm_workspace(B: int, D: int, Cc: int, device) -> Optional[torch.Tensor]:
     key = (torch.device(device).index or 0, torch.cuda.current_stream(device).cuda_stream)
     t = _WS.get(key)
     if t is None or t.numel() < n:
-        t = torch.zeros(n, dtype=torch.uint8, device=device)  # zeroed once; kernels keep the tickets zero
+        t = torch.empty(n, dtype=torch.uint8, device=device)
         _WS[key] = t
     return t
 
@@ -155,7 +157,7 @@ def softmax_ce(z, iif, label, *, class_weight=None, sample_weight=None, ignore_i
     r["lse"] = torch.empty(B, dtype=torch.float32, device=dev) if want_lse else None
     if B == 0:
         return r
-    tk = ticket(dev)
+    tk = loss_scratch(dev, B)
     _lib.check(_lib.load().iif_softmax_ce_fwd_bwd(
         _ptr(z), _ld(z), _ptr(iif), _ptr(label), _ptr(cw), _ptr(sw), int(ignore_index), float(scale), B, Cc,
         _ptr(r["loss_i"]), _ptr(r["loss_sum"]), _ptr(r["dz_f32"]), Cc, _ptr(r["dz_bf16"]), pad8(Cc), _ptr(r["lse"]),
@@ -198,7 +200,7 @@ def sigmoid_bce(z, label, *, pos_weight=None, col_weight=None, sample_weight=Non
     _lib.check(_lib.load().iif_sigmoid_bce_fwd_bwd(
         _ptr(z), _ld(z), _ptr(label), _ptr(pw), _ptr(colw), _ptr(sw), int(ignore_index), float(scale), B, Cc,
         _ptr(r["loss_elem"]), Cc, _ptr(r["loss_i"]), _ptr(r["loss_sum"]), _ptr(r["dz_f32"]), Cc, _ptr(r["dz_bf16"]),
-        pad8(Cc), _ptr(ticket(dev)), _stream(dev)), "sigmoid_bce_fwd_bwd")
+        pad8(Cc), _ptr(loss_scratch(dev, B)), _stream(dev)), "sigmoid_bce_fwd_bwd")
     return r
 
 
@@ -331,6 +333,29 @@ def linear_bwd_dw(dz, x, alpha=None):
     return dw
 
 
+def linear_bwd(dz, x, w, alpha=None, *, need_dx=True, need_db=True, dx_bf16=False):
+    """AddmmBackward of fc_cls in ONE launch (bf16 tcgen05): returns (dX | None, dW, db | None)."""
+    dz = _bf16_rows(dz, "dz")
+    x = _bf16_rows(x, "x")
+    w = _bf16_rows(w, "w")
+    B, Cc = dz.shape
+    D = x.shape[1]
+    if tuple(w.shape) != (Cc, D) or x.shape[0] != B:
+        raise ValueError("linear_bwd: shape mismatch")
+    dev = dz.device
+    al = _alpha(alpha, dev)
+    dx = torch.empty(B, D, dtype=torch.bfloat16 if dx_bf16 else torch.float32, device=dev) if need_dx else None
+    flat = torch.empty(Cc * D + (Cc if need_db else 0), dtype=torch.float32, device=dev)
+    dw = flat[:Cc * D].view(Cc, D)
+    db = flat[Cc * D:] if need_db else None
+    ws = gemm_workspace(B, D, Cc, dev)
+    _lib.check(_lib.load().iif_linear_bwd_bf16(
+        _ptr(dz), _ld(dz), _ptr(x), _ld(x), _ptr(w), _ld(w), _ptr(al), _ptr(dx),
+        _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32, D, _ptr(dw), D, _ptr(db), B, D, Cc, _ptr(ws),
+        0 if ws is None else ws.numel(), _stream(dev)), "linear_bwd_bf16")
+    return dx, dw, db
+
+
 class HeadStep:
     """Pre-allocated buffers + one C call (`iif_head_fwd_bwd_bf16`) per head step.
 
@@ -338,7 +363,7 @@ class HeadStep:
     once so the step can be captured in a CUDA graph.  dW and db live in ONE flat fp32 buffer
     (`grad_flat`) so the data-parallel all-reduce of the head's parameter gradients is one message."""
 
-    def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False):
+    def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False, ws=None):
         dev = torch.device(device)
         self.B, self.D, self.C, self.device = B, D, Cc, dev
         f32, i32 = torch.float32, torch.int32
@@ -353,12 +378,14 @@ class HeadStep:
         self.argmax = torch.empty(B, dtype=i32, device=dev) if want_acc else None
         self.rank = torch.empty(B, dtype=i32, device=dev) if want_acc else None
         self.acc_counts = torch.zeros(2, dtype=i32, device=dev) if want_acc else None
-        self.ticket = torch.zeros(1, dtype=i32, device=dev)
+        self.scratch = torch.zeros((int(_lib.load().iif_loss_scratch_bytes(B)) + 3) // 4, dtype=i32, device=dev)
         n = int(_lib.load().iif_gemm_ws_bytes(B, D, Cc))
-        self.ws = torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
+        if ws is not None and ws.numel() < n:
+            raise ValueError("HeadStep: shared workspace too small")
+        self.ws = ws if ws is not None else torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
         self.ws_bytes = n
         self.dx_dtype = _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32
-        self.launches_per_step = 3 + (1 if need_dx else 0) + (1 if need_db else 0)
+        self.launches_per_step = 3
         self._args = None
         self._keep = None
 
@@ -398,7 +425,7 @@ class HeadStep:
         a.argmax = None if self.argmax is None else self.argmax.data_ptr()
         a.rank = None if self.rank is None else self.rank.data_ptr()
         a.acc_counts = None if self.acc_counts is None else self.acc_counts.data_ptr()
-        a.ticket = self.ticket.data_ptr()
+        a.scratch = self.scratch.data_ptr()
         a.ws, a.ws_bytes = self.ws.data_ptr(), self.ws_bytes
         self._args = a
         self._keep = (x, w, bias, iif, label, class_weight, sample_weight)
@@ -428,14 +455,8 @@ class HeadStep:
                ("softmax_ce_fwd_bwd", lambda: lib.iif_softmax_ce_fwd_bwd(
                    p(a.z), a.ldz, p(a.iif), p(a.label), p(a.class_weight), p(a.sample_weight), a.ignore_index, a.scale,
                    a.B, a.C, p(a.loss_i), p(a.loss_sum), None, 0, p(a.dz_bf16), a.lddz, None, p(a.argmax), p(a.rank),
-                   p(a.acc_counts), p(a.ticket), st()))]
-        if self.db is not None:
-            out.append(("colsum_db", lambda: lib.iif_colsum(p(a.dz_bf16), _lib.DTYPE_BF16, a.lddz, None, a.B, a.C,
-                                                            p(a.db), st())))
-        if self.dx is not None:
-            out.append(("linear_bwd_dx_bf16", lambda: lib.iif_linear_bwd_dx_bf16(
-                p(a.dz_bf16), a.lddz, p(a.w), a.ldw, None, p(a.dx), a.dx_dtype, a.lddx, a.B, a.D, a.C, p(a.ws),
-                a.ws_bytes, st())))
-        out.append(("linear_bwd_dw_bf16", lambda: lib.iif_linear_bwd_dw_bf16(
-            p(a.dz_bf16), a.lddz, p(a.x), a.ldx, None, p(a.dw), a.lddw, a.B, a.D, a.C, p(a.ws), a.ws_bytes, st())))
+                   p(a.acc_counts), p(a.scratch), st()))]
+        out.append(("linear_bwd_bf16", lambda: lib.iif_linear_bwd_bf16(
+            p(a.dz_bf16), a.lddz, p(a.x), a.ldx, p(a.w), a.ldw, None, p(a.dx), a.dx_dtype, a.lddx, p(a.dw), a.lddw,
+            p(a.db), a.B, a.D, a.C, p(a.ws), a.ws_bytes, st())))
         return out

@@ -103,7 +103,9 @@ IIF_API int iif_weights_from_counts(const int64_t* counts, int64_t num_classes, 
  * cls/custom.py:28-36; seg/mmdet/models/losses/iif_loss.py:187-200, losses/utils.py:42-55.
  * scale = 1/B (cls 'mean'), 1 ('sum'/'none'), loss_weight/avg_factor or loss_weight/B (mmdet).
  * acc_counts[0..1] (optional) = #{rank_i < 1}, #{rank_i < 5} (cls/utils.py:165-179).
- * `ticket`: one int32 device word, zero on entry, left zero on exit (inter-CTA ordering).
+ * `scratch`: iif_loss_scratch_bytes(B) device bytes whose first int32 is zero on entry (left zero on
+ * exit): per-CTA partial sums for the deterministic grid-wide reduction; required with loss_sum /
+ * acc_counts.
  * Alignment: z and dz rows may use any leading dimension; 128-bit access is used when the base
  * pointers are 16-byte aligned and ldz / lddz / C are multiples of 4 (8 for bf16 dz).
  * Supported C: 1..32768. */
@@ -112,7 +114,8 @@ IIF_API int iif_softmax_ce_fwd_bwd(const float* z, int64_t ldz, const float* iif
                            int64_t ignore_index, float scale, int64_t B, int64_t C, float* loss_i,
                            float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
                            int64_t lddz_bf16, float* lse, int32_t* argmax, int32_t* rank,
-                           int32_t* acc_counts, int32_t* ticket, void* stream);
+                           int32_t* acc_counts, int32_t* scratch, void* stream);
+IIF_API size_t iif_loss_scratch_bytes(int64_t B);
 
 /* out = softmax(z * iif) per row (seg/mmdet/models/losses/iif_loss.py:76) or, with
  * softmax == 0, out = z * iif (cls/custom.py:38, infer=True).  argmax/rank (optional) are taken
@@ -139,7 +142,7 @@ IIF_API int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_t* 
                             const float* sample_weight, int64_t ignore_index, float scale,
                             int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
                             float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
-                            int64_t lddz_bf16, int32_t* ticket, void* stream);
+                            int64_t lddz_bf16, int32_t* scratch, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * small elementwise helpers on [rows, cols] matrices
@@ -159,8 +162,8 @@ IIF_API int iif_colsum(const void* dz, int dz_dtype, int64_t lddz, const float* 
 /* ---------------------------------------------------------------------------------------------
  * (a)/(c) fc_cls GEMMs.  *_bf16: tcgen05.mma (TMEM accumulators, TMA-fed), bf16 operands, fp32
  * accumulation.  *_f32: FFMA, fp32 operands (the 1e-5 parity mode).
- * `ws`: workspace of at least iif_gemm_ws_bytes(...) bytes, ZEROED once by the caller (the kernels
- * leave its ticket area zeroed); may be NULL when iif_gemm_ws_bytes returns 0.
+ * `ws`: workspace of at least iif_gemm_ws_bytes(...) bytes (split-K partial tiles exchanged inside a
+ * thread-block cluster; contents need no initialisation); may be NULL when iif_gemm_ws_bytes returns 0.
  * bf16 alignment: base pointers 16 bytes; leading dimensions of bf16 operands multiples of 8.
  * ------------------------------------------------------------------------------------------- */
 
@@ -191,6 +194,13 @@ IIF_API int iif_linear_bwd_dw_f32(const float* dz, int64_t lddz, const float* x,
                           const float* alpha_dev, float* dw, int64_t lddw, int64_t B, int64_t D,
                           int64_t C, void* stream);
 
+/* dX, dW and db of AddmmBackward in ONE launch (they share dZ and together fill the SMs):
+ *   dX[B,D] = alpha dZ W (skipped when dx == NULL: frozen backbone, cls/train.py:123-145),
+ *   dW[C,D] = alpha dZ^T X,  db[C] = alpha sum_i dZ[i,:] (optional; computed on the tensor cores). */
+IIF_API int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
+                        const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw, int64_t lddw,
+                        float* db, int64_t B, int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream);
+
 /* Workspace (bytes) the three bf16 GEMMs of a head of this shape may need (max over the three). */
 IIF_API size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C);
 
@@ -219,11 +229,12 @@ typedef struct iif_head_args {
   float* db;                          /* fp32 [C] or NULL */
   int32_t* argmax; int32_t* rank; int32_t* acc_counts;
   /* scratch */
-  int32_t* ticket;                    /* 1 zeroed int32 */
-  void* ws; size_t ws_bytes;          /* iif_gemm_ws_bytes(B,D,C), zeroed once */
+  int32_t* scratch;                   /* iif_loss_scratch_bytes(B), first int32 zero */
+  void* ws; size_t ws_bytes;          /* iif_gemm_ws_bytes(B,D,C) */
 } iif_head_args;
 
-/* Launches the 4-5 kernels of one head step on `stream` (cls/train.py:66-77 collapsed to the head;
+/* Launches the 3 kernels of one head step on `stream` (fc_cls GEMM; fused loss; dX+dW+db GEMM group),
+ * chained by programmatic dependent launch (cls/train.py:66-77 collapsed to the head;
  * seg/.../bbox_head.py:118 + :269-274 + autograd). */
 IIF_API int iif_head_fwd_bwd_bf16(const iif_head_args* args, void* stream);
 

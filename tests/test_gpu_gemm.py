@@ -80,6 +80,27 @@ def test_gemm_bf16_tcgen05(ops, B, D, C):
     assert rel_err(N(dx), dx32) < TOL_BF16 and rel_err(N(dw), 2.0 * dw32) < TOL_BF16
 
 
+@pytest.mark.parametrize("B,D,C", SHAPES + [(2048, 512, 1000), (64, 2048, 10000)])
+def test_linear_bwd_grouped(ops, B, D, C):
+    """dX + dW + db in one launch (db on the tensor cores via the ones tile) vs the oracle on the
+    same bf16 operands; alpha read from the device; dX optional (frozen backbone)."""
+    x, w, b, counts, y = head_inputs(B, D, C, seed=B + C + 2)
+    rng = np.random.default_rng(3)
+    dz = (rng.standard_normal((B, C)) / B).astype(np.float32)
+    xb, wb, dzb = bf16_round(x), bf16_round(w), bf16_round(dz)
+    bf = torch.bfloat16
+    dzt = ops.scale_rows(T(dz), None, bf16=True, pad_ld=True)
+    dxr, dwr, dbr = ho.linear_bwd(dzb, xb, wb)
+    dx, dw, db = ops.linear_bwd(dzt, T(x, bf), T(w, bf), alpha=T(np.float32(0.5)))
+    assert rel_err(N(dx), 0.5 * dxr) < 2e-5
+    assert rel_err(N(dw), 0.5 * dwr) < 2e-5
+    assert rel_err(N(db), 0.5 * dbr) < 2e-5
+    dx2, dw2, db2 = ops.linear_bwd(dzt, T(x, bf), T(w, bf), need_dx=False, need_db=False)
+    assert dx2 is None and db2 is None and rel_err(N(dw2), dwr) < 2e-5
+    dx3, dw3, db3 = ops.linear_bwd(dzt, T(x, bf), T(w, bf), dx_bf16=True)
+    assert dx3.dtype == bf and rel_err(N(dx3), dxr) < 8e-3 and torch.equal(dw3, dw2)
+
+
 def test_gemm_bf16_deterministic_and_ticket_reset(ops):
     """Split-K partial sums are added in split order by the last CTA: run-to-run bit-identical, and
     the self-resetting tickets allow back-to-back launches on one workspace."""

@@ -1,0 +1,16 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
+for f in test_gpu_gemm test_gpu_loss test_gpu_modules test_gpu_hist; do
+  timeout 900 python -m pytest tests/$f.py -q -m gpu --timeout 300 > gpurun_out/$f.log 2>&1
+  echo "$f exit $?" >> gpurun_out/summary.txt
+  grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/$f.log | head -20
+done
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/summary.txt
+timeout 600 python bench.py > gpurun_out/bench.log 2>&1; echo "bench exit $?" >> gpurun_out/summary.txt
+tail -1 gpurun_out/bench.log
+timeout 300 python bench.py --steps 48 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
+  python bench.py --steps 48 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+echo "ncu exit $?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt
