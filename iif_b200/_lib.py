@@ -55,6 +55,7 @@ SIGNATURES = {
     "iif_linear_bwd_dw_f32": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "iif_linear_bwd_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _i64, _i64, _p,
                                    _sz, _p]),
+    "iif_debug_timing": (None, [_p]),
     "iif_gemm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "iif_head_fwd_bwd_bf16": (_i32, [C.POINTER(HeadArgs), _p]),
 }

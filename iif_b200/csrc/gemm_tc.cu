@@ -71,8 +71,17 @@ struct TcProblem {
 struct TcGroup {
   int nprob, stages, cluster;
   int cta_begin[3];
+  long long* dbg;                        // optional per-CTA phase timestamps (iif_debug_timing)
   TcProblem p[2];
 };
+
+__device__ __forceinline__ void stamp(const TcGroup& g, int slot) {
+  if (g.dbg) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.dbg[(int64_t)blockIdx.x * 16 + slot] = t;
+  }
+}
 
 __host__ __device__ inline int smem_bytes_for(int stages) { return stages * STAGE_BYTES + ONES_BYTES + 256 + 1024; }
 
@@ -126,6 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) stamp(g, 0);
   const int pi = (g.nprob > 1 && (int)blockIdx.x >= g.cta_begin[1]) ? 1 : 0;
   const TcProblem& P = g.p[pi];
   const CUtensorMap* tmA = pi ? &tmA1 : &tmA0;
@@ -167,8 +177,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
 
+  if (threadIdx.x == 0) stamp(g, 1);
   ptx::griddep_launch_dependents();      // the next kernel may start its own prologue now
   ptx::griddep_wait();                   // ... and ours ends here: the producer kernel's data is visible
+  if (threadIdx.x == 0) stamp(g, 2);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -193,6 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
+      stamp(g, 3);                       // all TMA loads issued
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
@@ -207,6 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
+        if (kb == kb_begin) stamp(g, 4);   // first stage landed
+        if (kb == kb_end - 1) stamp(g, 5); // last stage landed
         const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < TILE_K / 16; ++k) {
@@ -230,6 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int row = q * 32 + lane;           // row inside the tile
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
+    if (threadIdx.x == 128) stamp(g, 6);   // accumulator complete
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float* srow = reinterpret_cast<float*>(smem_gen) + row * LDS;
 #pragma unroll 1
@@ -250,6 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();                           // staging tile complete; TMEM no longer needed
+  if (threadIdx.x == 0) stamp(g, 7);
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -275,7 +292,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     float* dbp = do_db ? P.db_partial + (int64_t)(tile / P.tiles_n) * P.splits * TILE_M : nullptr;
     if (do_db && threadIdx.x < TILE_M) __stcg(dbp + split * TILE_M + threadIdx.x, stg[threadIdx.x * LDS + BN]);
+    if (threadIdx.x == 0) stamp(g, 8);
     ptx::cluster_sync();                     // release our partial / acquire the other splits'
+    if (threadIdx.x == 0) stamp(g, 9);
     const int rps = (TILE_M + P.splits - 1) / P.splits;
     const int r0 = split * rps, r1 = min(TILE_M, r0 + rps);
     for (int idx = threadIdx.x; idx < (r1 - r0) * F4; idx += 256) {
@@ -296,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       P.db_out[m0 + r0 + threadIdx.x] = acc * alpha;
     }
   }
+  if (threadIdx.x == 0) stamp(g, 10);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,6 +443,8 @@ static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, float*
   return IIF_OK;
 }
 
+static long long* g_dbg = nullptr;   // iif_debug_timing
+
 // Launch one or two problems in one grid.
 static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes, cudaStream_t st) {
   static bool configured = false;
@@ -484,6 +506,7 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
   g.nprob = nprob;
   g.cluster = cluster;
   g.stages = MAX_STAGES;
+  g.dbg = g_dbg;
   if (nprob == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
 
   cudaLaunchConfig_t cfg{};
@@ -541,6 +564,8 @@ static GemmDesc desc_dw(const void* dz, int64_t lddz, const void* x, int64_t ldx
 }  // namespace iif
 
 using namespace iif;
+
+extern "C" void iif_debug_timing(long long* buf) { g_dbg = buf; }
 
 extern "C" size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C) {
   if (B <= 0 || D <= 0 || C <= 0) return 0;

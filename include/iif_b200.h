@@ -201,6 +201,10 @@ IIF_API int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int
                         const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw, int64_t lddw,
                         float* db, int64_t B, int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream);
 
+/* Debug hook: when `buf` (device, 16 int64 per CTA of the next tensor-core launches) is non-NULL every CTA
+ * records %globaltimer at its phase boundaries (tools/tc_timing.py); NULL switches it off. */
+IIF_API void iif_debug_timing(long long* buf);
+
 /* Workspace (bytes) the three bf16 GEMMs of a head of this shape may need (max over the three). */
 IIF_API size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C);
 

@@ -98,7 +98,7 @@ def test_linear_bwd_grouped(ops, B, D, C):
     dx2, dw2, db2 = ops.linear_bwd(dzt, T(x, bf), T(w, bf), need_dx=False, need_db=False)
     assert dx2 is None and db2 is None and rel_err(N(dw2), dwr) < 2e-5
     dx3, dw3, db3 = ops.linear_bwd(dzt, T(x, bf), T(w, bf), dx_bf16=True)
-    assert dx3.dtype == bf and rel_err(N(dx3), dxr) < 8e-3 and torch.equal(dw3, dw2)
+    assert dx3.dtype == bf and rel_err(N(dx3), dxr) < 8e-3 and rel_err(N(dw3), dwr) < 2e-5
 
 
 def test_gemm_bf16_deterministic_and_ticket_reset(ops):
