@@ -176,7 +176,7 @@ def main():
     S = max(2, int(-(-2.0 * L2_BYTES // per_set)))           # rotating sets: footprint >= 2 x L2
     prob = torch.from_numpy(cnt / cnt.sum())
     sets = []
-    shared_ws = torch.empty(max(int(ops._lib.load().iif_gemm_ws_bytes(B, D, C)), 1), dtype=torch.uint8, device=dev)
+    shared_ws = torch.zeros(max(int(ops._lib.load().iif_gemm_ws_bytes(B, D, C)), 1), dtype=torch.uint8, device=dev)
     for s in range(S):
         x = torch.randn(B, D, generator=g).to(dev).to(torch.bfloat16)
         w = ((torch.rand(C, D, generator=g) * 2 - 1) / D ** 0.5).to(dev).to(torch.bfloat16)

@@ -1,6 +1,6 @@
 // (a)/(c) fc_cls GEMMs on the 5th-generation tensor cores: tcgen05.mma with the accumulator in
 // TMEM, operands staged in shared memory by TMA through an mbarrier ring, one elected thread
-// issuing the MMAs, a 4-warp TMEM drain and a block-wide coalesced epilogue.
+// issuing the MMAs, an 8-warp TMEM drain and a TMA-store epilogue.
 //
 //   OUT[M,N] = alpha * A[M,K] . B[N,K]^T (+ bias[n]),  out2 = OUT * col_scale[n]
 //
@@ -14,23 +14,33 @@
 // One launch runs a GROUP of up to two problems (dX and dW share a launch: they depend on the same
 // dZ and together fill the 148 SMs); blockIdx.x -> (problem, tile, K split).
 //
-// Tile: 128 x 128 x 64 per CTA, 128-byte swizzle, ring of `stages` 32 KB stages.  The head shapes
-// are small (ImageNet-LT: 256 x 1000 x 2048), so K is split across the CTAs of a thread-block
-// CLUSTER (cluster size = number of K splits, <= 8): every CTA parks its fp32 partial tile in an
-// L2-resident workspace, the cluster barrier (release/acquire) orders the exchange, and then EVERY
-// CTA of the cluster reduces 1/splits of the tile's rows in split order -- a parallel,
-// deterministic reduction with no float atomics, no spin waits and no serial tail.
+// Tile: 128 x 128 x 64 per CTA, 128-byte swizzle, ring of 3 x 32 KB stages => ~100 KB of shared
+// memory and 256 TMEM columns per CTA, TWO CTAs per SM (296 resident CTAs): the drain / store of one
+// CTA overlaps the TMA + MMA stream of its neighbour, and a programmatically launched successor
+// kernel finds room for its prologue.
 //
-// Epilogue: the 4 drain warps move TMEM -> registers -> a padded staging tile in (recycled) stage
-// memory; after one block barrier all 256 threads write 512-byte row segments (one warp = one row of
-// the tile), so partials, fp32 / bf16 outputs and the IIF-scaled second output are fully coalesced.
+// Split-K for the small head shapes (ImageNet-LT: 256 x 1000 x 2048 has only 16 output tiles): the
+// CTAs of one tile park their fp32 partial tiles in an L2-resident workspace (register -> global,
+// in a layout that is coalesced for both the writer and the reader), meet at a per-tile arrival
+// counter (release / acquire at gpu scope) and then EVERY CTA reduces 1/splits of the tile's rows
+// in split order: parallel, deterministic, no float atomics, no serial tail.  The counters are
+// self-resetting; the host only enables split-K when the whole grid is co-resident.
+// (Round-1 first version used a thread-block cluster of 8 for this; 8-CTA clusters schedule at most
+// ~14 clusters at once on B200's GPCs, so the 16-tile forward ran as two waves -- see profiles/.)
+//
+// Epilogue, unsplit tiles: each warp moves its 32 x 64 accumulator slab TMEM -> registers -> (alpha,
+// bias) -> a 128B-swizzled box in recycled stage memory -> one TMA store per 32 x 32 fp32 box
+// (bank-conflict-free, full 128-byte lines, tile tails clipped by the TMA unit).  Outputs the TMA
+// unit cannot address (row pitch not a multiple of 16 bytes, e.g. Places-LT C = 365, or the second
+// IIF-scaled output) go through a warp-private transposing staging slab and coalesced row stores.
 //
 // Bias gradient on the tensor cores: in the dW product the CTAs of the first tile column issue one
 // extra N=16 MMA per k-step against a constant tile of ones, so db[c] = sum_b dZ[b,c] * 1 falls out
 // of the same operand stream into 16 spare TMEM columns -- no column-sum kernel, no extra HBM read.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warp 3 = ones tile, warps 4..7 = TMEM drain (warp w may only touch TMEM lanes 32*(w%4) .. +31).
+// warp 3 = ones tile + bias/scale staging; then ALL 8 warps drain (warp w owns TMEM lanes
+// 32*(w%4).. and accumulator columns 64*(w/4)..).
 //
 // Every kernel begins with griddepcontrol.launch_dependents / .wait (programmatic dependent
 // launch): the prologue (barrier init, TMEM alloc, tensor-map prefetch) overlaps the tail of the
@@ -51,25 +61,32 @@ constexpr int BN = 128;
 constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * TILE_K * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int LDS = BN + 4;           // staging tile row pitch (floats): conflict-free float4 rows
-constexpr int MAX_STAGES = 6;
-constexpr int MAX_SPLITS = 8;         // portable cluster size
+constexpr int STAGES = 3;
+constexpr int MAX_SPLITS = 8;
 constexpr int ONES_BYTES = 2048;      // 16 rows x 128 B of bf16 1.0 (K-major B operand of the db MMA)
 constexpr int TMEM_COLS = 256;        // BN accumulator columns + 16 for db (power of two)
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + BAR_BYTES + 2 * BN * 4 + 1024;
+constexpr int GEN_PITCH = 65;         // generic epilogue: warp-private 32 x 65 float slab
+constexpr int WS_HEADER = 4096;       // split-K counters: 2 problems x 256 tiles x {arrive, done}
+constexpr int TILE_F4 = TILE_M * BN / 4;
+static_assert(8 * 32 * GEN_PITCH * 4 <= STAGES * STAGE_BYTES, "generic staging must fit in the stage ring");
+static_assert(TILE_M * BN * 4 <= STAGES * STAGE_BYTES, "TMA-store staging must fit in the stage ring");
 
 struct TcProblem {
   int M, N, K;
   int tiles_m, tiles_n, kb_total, kb_per_split, splits;
   int a_mn, b_mn;
-  const float* alpha; const float* bias; const float* col_scale; int bias_vec;
-  void* out; int out_bf16; int out_vec; int64_t ldo;
-  float* out2; int out2_vec; int64_t ldo2;
-  float* partial;                                   // [tiles][splits][TILE_M][BN] fp32
+  const float* alpha; const float* bias; const float* col_scale;
+  void* out; int out_bf16; int64_t ldo; int epi_tma;
+  float* out2; int64_t ldo2;
+  float4* partial;                                  // [tiles][splits][TILE_F4] fp32x4, layout part_idx()
+  int* counters;                                    // [tiles][2]: arrive, done (zero between launches)
   float* db_out; float* db_partial;                 // dW only: db[m] (and [tiles_m][splits][TILE_M] partials)
 };
 
 struct TcGroup {
-  int nprob, stages, cluster;
+  int nprob;
   int cta_begin[3];
   long long* dbg;                        // optional per-CTA phase timestamps (iif_debug_timing)
   TcProblem p[2];
@@ -83,56 +100,59 @@ __device__ __forceinline__ void stamp(const TcGroup& g, int slot) {
   }
 }
 
-__host__ __device__ inline int smem_bytes_for(int stages) { return stages * STAGE_BYTES + ONES_BYTES + 256 + 1024; }
+// Partial-tile layout (float4 units): 8-row groups, inside a group 32 column-chunks x 8 rows.
+//  - drain (lane = row, fixed chunk j): 8 lanes x 16 B contiguous -> four full 128 B lines per warp store
+//  - reduce (consecutive threads = consecutive float4): fully coalesced; a warp then owns 8 rows x 4
+//    chunks = 64 contiguous output bytes per row
+__device__ __forceinline__ int part_idx(int j, int row) { return (((row >> 3) * 32 + j) << 3) + (row & 7); }
 
-__device__ __forceinline__ void emit4(const TcProblem& P, int m, int n, float4 v, float alpha) {
-  // one thread = 4 consecutive columns of one output row
+// One float4 of the final output: alpha, bias, store (fp32 / bf16), optional scaled copy.  Bounds-checked.
+__device__ __forceinline__ void emit4(const TcProblem& P, int m, int n, float4 v, float alpha, const float* s_bias,
+                                      const float* s_scale, int nl) {
   if (m >= P.M || n >= P.N) return;
-  float r[4] = {v.x * alpha, v.y * alpha, v.z * alpha, v.w * alpha};
+  float r[4] = {v.x * alpha + s_bias[nl], v.y * alpha + s_bias[nl + 1], v.z * alpha + s_bias[nl + 2],
+                v.w * alpha + s_bias[nl + 3]};
   const bool full = n + 4 <= P.N;
-  if (P.bias) {
-    if (full && P.bias_vec) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n));
-      r[0] += b.x; r[1] += b.y; r[2] += b.z; r[3] += b.w;
-    } else {
-      for (int j = 0; j < 4; ++j) if (n + j < P.N) r[j] += __ldg(P.bias + n + j);
-    }
-  }
   if (P.out) {
     if (P.out_bf16) {
       uint16_t* o = reinterpret_cast<uint16_t*>(P.out) + (int64_t)m * P.ldo + n;
-      if (full && P.out_vec) stg_stream2(o, pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
+      if (full && (P.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(P.out) & 7u) == 0)
+        stg_stream2(o, pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
       else for (int j = 0; j < 4; ++j) if (n + j < P.N) o[j] = bf16_bits(r[j]);
     } else {
       float* o = reinterpret_cast<float*>(P.out) + (int64_t)m * P.ldo + n;
-      if (full && P.out_vec) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
+      if (full && (P.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(P.out) & 15u) == 0)
+        stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
       else for (int j = 0; j < 4; ++j) if (n + j < P.N) o[j] = r[j];
     }
   }
   if (P.out2) {
     float* o = P.out2 + (int64_t)m * P.ldo2 + n;
-    for (int j = 0; j < 4; ++j) r[j] *= (n + j < P.N) ? __ldg(P.col_scale + n + j) : 0.f;
-    if (full && P.out2_vec) stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
+    for (int j = 0; j < 4; ++j) r[j] *= s_scale[nl + j];
+    if (full && (P.ldo2 & 3) == 0 && (reinterpret_cast<uintptr_t>(P.out2) & 15u) == 0)
+      stg_stream4(o, make_float4(r[0], r[1], r[2], r[3]));
     else for (int j = 0; j < 4; ++j) if (n + j < P.N) o[j] = r[j];
   }
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                const __grid_constant__ TcGroup g) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  const int stages = g.stages;
-  const uint32_t ones_base = smem_base + stages * STAGE_BYTES;      // 1024-byte aligned
+  const uint32_t ones_base = smem_base + STAGES * STAGE_BYTES;      // 1024-byte aligned
   const uint32_t bar_base = ones_base + ONES_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAX_STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base + BAR_BYTES - smem_base));
+  float* s_scale = s_bias + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) stamp(g, 0);
@@ -140,14 +160,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const TcProblem& P = g.p[pi];
   const CUtensorMap* tmA = pi ? &tmA1 : &tmA0;
   const CUtensorMap* tmB = pi ? &tmB1 : &tmB0;
+  const CUtensorMap* tmO = pi ? &tmO1 : &tmO0;
   const int local = (int)blockIdx.x - g.cta_begin[pi];
   const int split = local % P.splits;
   const int tile = local / P.splits;
-  const bool has_work = tile < P.tiles_m * P.tiles_n;
-  if (!has_work) {                       // padding CTA of a cluster: only keep the barrier balanced
-    if (P.splits > 1) ptx::cluster_sync();
-    return;
-  }
   const int n0 = (tile % P.tiles_n) * BN, m0 = (tile / P.tiles_n) * TILE_M;
   const int kb_begin = split * P.kb_per_split;
   const int kb_end = min(P.kb_total, kb_begin + P.kb_per_split);
@@ -156,9 +172,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(tmA);
     ptx::prefetch_tensormap(tmB);
+    if (P.epi_tma) ptx::prefetch_tensormap(tmO);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < stages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
@@ -203,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         } else {
           ptx::tma_load_2d(sb, tmB, full_bar(stage), k0, n0);
         }
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       stamp(g, 3);                       // all TMA loads issued
     }
@@ -233,89 +250,180 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             ptx::umma_bf16(tmem_base + BN, da, ptx::make_smem_desc_sw128(ones_base + k * 32, 16, 1024), idesc_db, accum);
         }
         ptx::umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       ptx::umma_commit(tmem_full_bar);       // accumulator complete
     }
-  } else if (warp < 4) {
-    // idle until the epilogue
+  } else if (warp == 3) {
+    // epilogue vectors of this tile's 128 columns (read after the dependency wait: parameters)
+    for (int i = lane; i < BN; i += 32) {
+      const int n = n0 + i;
+      s_bias[i] = (P.bias && n < P.N) ? __ldg(P.bias + n) : 0.f;
+      s_scale[i] = (P.col_scale && n < P.N) ? __ldg(P.col_scale + n) : 0.f;
+    }
+  }
+  const float alpha = P.alpha ? __ldg(P.alpha) : 1.f;
+  __syncthreads();                           // roles issued; s_bias / s_scale visible
+
+  // ===================== drain: all 8 warps =====================
+  const int q = warp & 3, h = warp >> 2;     // TMEM lane quarter, accumulator column half
+  const int row = q * 32 + lane;             // row inside the tile
+  ptx::mbar_wait(tmem_full_bar, 0);
+  ptx::tc_fence_after();
+  if (threadIdx.x == 0) stamp(g, 6);         // accumulator complete: the stage ring is free for staging
+  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 64);
+
+  if (P.splits == 1) {
+    if (P.epi_tma) {
+      // ---- registers -> swizzled box -> TMA store (per warp; no block barrier)
+      const uint32_t wbase = smem_base + (uint32_t)warp * (P.out_bf16 ? 4096u : 8192u);
+      const uint32_t rbase = wbase + (uint32_t)lane * 128u;
+      const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+        const float* bs = s_bias + h * 64 + c * 32;
+        if (P.out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {      // 8 values -> one 16-byte chunk
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              pk[e] = pack_bf16x2(__uint_as_float(r[8 * j + 2 * e]) * alpha + bs[8 * j + 2 * e],
+                                  __uint_as_float(r[8 * j + 2 * e + 1]) * alpha + bs[8 * j + 2 * e + 1]);
+            ptx::sts128(rbase + ((((uint32_t)(c * 4 + j)) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j);
+            ptx::sts128(rbase + (uint32_t)c * 4096u + ((((uint32_t)j) ^ sw) << 4),
+                        __float_as_uint(__uint_as_float(r[4 * j]) * alpha + b4.x),
+                        __float_as_uint(__uint_as_float(r[4 * j + 1]) * alpha + b4.y),
+                        __float_as_uint(__uint_as_float(r[4 * j + 2]) * alpha + b4.z),
+                        __float_as_uint(__uint_as_float(r[4 * j + 3]) * alpha + b4.w));
+          }
+        }
+      }
+      ptx::fence_proxy_async();              // generic-proxy smem writes -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        const int mr = m0 + q * 32, nc = n0 + h * 64;
+        if (mr < P.M) {
+          if (P.out_bf16) {
+            if (nc < P.N) ptx::tma_store_2d(tmO, wbase, nc, mr);
+          } else {
+            if (nc < P.N) ptx::tma_store_2d(tmO, wbase, nc, mr);
+            if (nc + 32 < P.N) ptx::tma_store_2d(tmO, wbase + 4096u, nc + 32, mr);
+          }
+        }
+        ptx::bulk_commit();
+      }
+    } else {
+      // ---- generic: warp-private transposing slab, then coalesced (bounds-checked) row stores
+      float* slab = reinterpret_cast<float*>(smem_gen) + warp * (32 * GEN_PITCH);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + c * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) slab[lane * GEN_PITCH + c * 32 + j] = __uint_as_float(r[j]);
+      }
+      __syncwarp();
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m0 + q * 32 + rr;
+        if (m >= P.M) break;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int nl = h * 64 + c * 32 + lane, n = n0 + nl;
+          if (n < P.N) {
+            const float v = slab[rr * GEN_PITCH + c * 32 + lane] * alpha + s_bias[nl];
+            if (P.out) {
+              if (P.out_bf16) reinterpret_cast<uint16_t*>(P.out)[(int64_t)m * P.ldo + n] = bf16_bits(v);
+              else reinterpret_cast<float*>(P.out)[(int64_t)m * P.ldo + n] = v;
+            }
+            if (P.out2) P.out2[(int64_t)m * P.ldo2 + n] = v * s_scale[nl];
+          }
+        }
+      }
+    }
+    if (do_db && h == 0) {                   // db of this row: first of the 16 equal columns
+      const uint32_t v = ptx::tmem_ld1(tmem_base + ((uint32_t)(q * 32) << 16) + BN);
+      ptx::tmem_ld_wait();
+      if (m0 + row < P.M) P.db_out[m0 + row] = __uint_as_float(v) * alpha;
+    }
   } else {
-    // ===================== drain: TMEM -> registers -> staging tile =====================
-    const int q = warp & 3;                  // TMEM lane quarter owned by this warp
-    const int row = q * 32 + lane;           // row inside the tile
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    if (threadIdx.x == 128) stamp(g, 6);   // accumulator complete
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* srow = reinterpret_cast<float*>(smem_gen) + row * LDS;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    // ---- split-K: partial tile -> L2 workspace, meet at the tile's counter, reduce 1/splits of the rows
+    float4* base = P.partial + (int64_t)tile * P.splits * TILE_F4;
+    float4* mine = base + (int64_t)split * TILE_F4;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
       uint32_t r[32];
-      ptx::tmem_ld32(taddr + c0, r);
+      ptx::tmem_ld32(taddr + c * 32, r);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(srow + c0 + j) =
-            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-    }
-    if (do_db) {                             // db partial of this row: first of the 16 equal columns
-      const uint32_t v = ptx::tmem_ld1(taddr + BN);
-      ptx::tmem_ld_wait();
-      srow[BN] = __uint_as_float(v);
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();                           // staging tile complete; TMEM no longer needed
-  if (threadIdx.x == 0) stamp(g, 7);
-  if (warp == 2) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-
-  // ===================== block-wide coalesced epilogue =====================
-  const float* stg = reinterpret_cast<const float*>(smem_gen);
-  const float alpha = P.alpha ? __ldg(P.alpha) : 1.f;
-  constexpr int F4 = BN / 4;                 // float4 per tile row: one warp covers one row
-  if (P.splits == 1) {
-    for (int idx = threadIdx.x; idx < TILE_M * F4; idx += 256) {
-      const int row = idx / F4, c4 = idx % F4;
-      emit4(P, m0 + row, n0 + c4 * 4, *reinterpret_cast<const float4*>(stg + row * LDS + c4 * 4), alpha);
-    }
-    if (do_db && threadIdx.x < TILE_M && m0 + (int)threadIdx.x < P.M)
-      P.db_out[m0 + threadIdx.x] = stg[threadIdx.x * LDS + BN] * alpha;
-  } else {
-    float4* base = reinterpret_cast<float4*>(P.partial) + (int64_t)tile * P.splits * (TILE_M * F4);
-    float4* mine = base + (int64_t)split * (TILE_M * F4);
-    for (int idx = threadIdx.x; idx < TILE_M * F4; idx += 256) {
-      const int row = idx / F4, c4 = idx % F4;
-      __stcg(mine + idx, *reinterpret_cast<const float4*>(stg + row * LDS + c4 * 4));
+      for (int j = 0; j < 8; ++j)
+        __stcg(mine + part_idx(h * 16 + c * 8 + j, row),
+               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                           __uint_as_float(r[4 * j + 3])));
     }
     float* dbp = do_db ? P.db_partial + (int64_t)(tile / P.tiles_n) * P.splits * TILE_M : nullptr;
-    if (do_db && threadIdx.x < TILE_M) __stcg(dbp + split * TILE_M + threadIdx.x, stg[threadIdx.x * LDS + BN]);
-    if (threadIdx.x == 0) stamp(g, 8);
-    ptx::cluster_sync();                     // release our partial / acquire the other splits'
-    if (threadIdx.x == 0) stamp(g, 9);
-    const int rps = (TILE_M + P.splits - 1) / P.splits;
-    const int r0 = split * rps, r1 = min(TILE_M, r0 + rps);
-    for (int idx = threadIdx.x; idx < (r1 - r0) * F4; idx += 256) {
-      const int row = r0 + idx / F4, c4 = idx % F4;
+    if (do_db && h == 0) {
+      const uint32_t v = ptx::tmem_ld1(tmem_base + ((uint32_t)(q * 32) << 16) + BN);
+      ptx::tmem_ld_wait();
+      __stcg(dbp + split * TILE_M + row, __uint_as_float(v));
+    }
+    int* arrive = P.counters + 2 * tile;
+    __syncthreads();                         // every thread's partial stores are issued ...
+    if (threadIdx.x == 0) {
+      stamp(g, 7);
+      __threadfence();                       // ... and made visible at gpu scope (cumulative) before the arrival
+      ptx::red_release_add(arrive, 1);
+      ptx::spin_until_ge(arrive, P.splits);
+      __threadfence();
+      stamp(g, 8);
+    }
+    __syncthreads();
+    const int gps = (TILE_M / 8 + P.splits - 1) / P.splits;          // 8-row groups per split
+    const int g0 = split * gps, g1 = min(TILE_M / 8, g0 + gps);
+    for (int grp = g0; grp < g1; ++grp) {
+      const int idx = grp * 256 + threadIdx.x;
       float4 t[MAX_SPLITS];
 #pragma unroll
       for (int s = 0; s < MAX_SPLITS; ++s)
-        if (s < P.splits) t[s] = __ldcg(base + (int64_t)s * (TILE_M * F4) + row * F4 + c4);
+        if (s < P.splits) t[s] = __ldcg(base + (int64_t)s * TILE_F4 + idx);
       float4 acc = t[0];
 #pragma unroll
       for (int s = 1; s < MAX_SPLITS; ++s)   // fixed split order: deterministic sum
         if (s < P.splits) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }
-      emit4(P, m0 + row, n0 + c4 * 4, acc, alpha);
+      const int j = threadIdx.x >> 3;
+      emit4(P, m0 + grp * 8 + (threadIdx.x & 7), n0 + 4 * j, acc, alpha, s_bias, s_scale, 4 * j);
     }
-    if (do_db && (int)threadIdx.x < r1 - r0 && m0 + r0 + (int)threadIdx.x < P.M) {
-      float acc = 0.f;
-      for (int s = 0; s < P.splits; ++s) acc += __ldcg(dbp + s * TILE_M + r0 + threadIdx.x);
-      P.db_out[m0 + r0 + threadIdx.x] = acc * alpha;
+    if (do_db) {
+      const int r0 = g0 * 8, r1 = g1 * 8;
+      if ((int)threadIdx.x < r1 - r0 && m0 + r0 + (int)threadIdx.x < P.M) {
+        float acc = 0.f;
+        for (int s = 0; s < P.splits; ++s) acc += __ldcg(dbp + s * TILE_M + r0 + threadIdx.x);
+        P.db_out[m0 + r0 + threadIdx.x] = acc * alpha;
+      }
+    }
+    __syncthreads();                         // all reads of the partials done
+    if (threadIdx.x == 0 && atomicAdd(arrive + 1, 1) == P.splits - 1) {   // last reader re-arms the counters
+      arrive[0] = 0;
+      arrive[1] = 0;
     }
   }
-  if (threadIdx.x == 0) stamp(g, 10);
+  ptx::tc_fence_before();
+  if (P.splits == 1 && P.epi_tma && lane == 0) ptx::bulk_wait_read0();   // staging must outlive the bulk reads
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+  if (threadIdx.x == 0) stamp(g, 9);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,25 +446,29 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; uint64_t inner, outer, ld; uint32_t box_outer;
+  const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer, f32;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer;
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+           box_outer == o.box_outer && f32 == o.f32;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
-    for (uint64_t v : {k.inner, k.outer, k.ld, (uint64_t)k.box_outer}) h = h * 1000003u ^ (size_t)v;
+    for (uint64_t v : {k.inner, k.outer, k.ld, (uint64_t)k.box_inner, (uint64_t)k.box_outer, (uint64_t)k.f32})
+      h = h * 1000003u ^ (size_t)v;
     return h;
   }
 };
 
-// bf16 row-major [outer, inner] with leading dimension ld; box = 64 (inner) x box_outer, 128B swizzle,
-// out-of-bounds elements read as zero (tile tails need no host padding).
-static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+// Row-major [outer, inner] tensor (bf16 or fp32) with leading dimension ld (elements); box =
+// box_inner x box_outer with a 128-byte inner extent, 128B swizzle.  Loads: out-of-bounds elements
+// read as zero (tile tails need no host padding); stores: out-of-bounds elements are not written.
+static int make_map(CUtensorMap* out, const void* ptr, bool f32, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{ptr, inner, outer, ld, box_outer};
+  const MapKey key{ptr, inner, outer, ld, box_inner, box_outer, f32 ? 1u : 0u};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -365,12 +477,12 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
   EncodeTiledFn enc = get_encode();
   if (!enc) return IIF_EDRIVER;
   const cuuint64_t dims[2] = {inner, outer};
-  const cuuint64_t strides[1] = {ld * 2};
-  const cuuint32_t box[2] = {64, box_outer};
+  const cuuint64_t strides[1] = {ld * (f32 ? 4u : 2u)};
+  const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return IIF_EDRIVER;
   std::lock_guard<std::mutex> g(mu);
   if (cache.size() > 4096) cache.clear();
@@ -378,14 +490,36 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
   return IIF_OK;
 }
 
+// Resident-CTA capacity of the device for this kernel (2 per SM on B200): the split-K rendezvous
+// needs every CTA of the grid on an SM at the same time.
+static int resident_capacity() {
+  static std::mutex mu;
+  static int caps[64] = {};              // per device ordinal; 0 = not yet queried
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  std::lock_guard<std::mutex> g(mu);
+  if (caps[dev] == 0) {
+    int sms = 0, per = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, gemm_tc_kernel, 256, SMEM_BYTES) != cudaSuccess) return 0;
+    caps[dev] = sms * per;
+  }
+  return caps[dev];
+}
+
 struct Plan {
-  int tiles_m, tiles_n, kb_total, kb_per_split, splits; size_t partial_bytes;
+  int tiles_m, tiles_n, kb_total, kb_per_split, splits;
+  size_t partial_bytes() const { return splits > 1 ? (size_t)tiles_m * tiles_n * splits * TILE_M * BN * 4 : 0; }
   size_t db_bytes() const { return splits > 1 ? (size_t)tiles_m * splits * TILE_M * 4 : 0; }   // 512-byte multiples
 };
 
-// K splits: the cluster size.  Cost model in k-block units: every CTA pays ~3 blocks of prologue +
-// epilogue, a split tile ~1.5 more for the exchange; CTAs run in waves of 148.
-static Plan make_plan(int64_t M, int64_t N, int64_t K, int other_ctas = 0) {
+// K splits.  Cost model in microseconds: a CTA pays ~2.5 us of latency (first TMA round trip, drain,
+// store), ~0.33 us per 32 KB k-block (doubled when two CTAs share an SM's L2 port), and a split tile
+// ~1 us + 0.05 us per split for the exchange.  Split-K is only legal while the whole grid is
+// co-resident (`cap` CTAs) and the per-problem counters fit the workspace header.
+static Plan make_plan(int64_t M, int64_t N, int64_t K, int other_ctas, int cap) {
   Plan p;
   p.tiles_m = (int)((M + TILE_M - 1) / TILE_M);
   p.tiles_n = (int)((N + BN - 1) / BN);
@@ -398,13 +532,14 @@ static Plan make_plan(int64_t M, int64_t N, int64_t K, int other_ctas = 0) {
     const int per = (p.kb_total + s - 1) / s;
     if ((p.kb_total + per - 1) / per != s) continue;            // s must be reachable exactly
     const int ctas = tiles * s + other_ctas;
-    const int waves = (ctas + kNumSMs - 1) / kNumSMs;
-    const double cost = waves * (per + 3.0 + (s > 1 ? 1.5 : 0.0));
+    if (s > 1 && (ctas > cap || tiles > 256)) break;
+    const int waves = cap > 0 ? (ctas + cap - 1) / cap : 1;
+    const double share = ctas > kNumSMs ? (ctas < 2 * kNumSMs ? (double)ctas / kNumSMs : 2.0) : 1.0;
+    const double cost = waves * (2.5 + per * 0.33 * share + (s > 1 ? 1.0 + 0.05 * s : 0.0));
     if (cost < best - 1e-9) { best = cost; best_s = s; }
   }
   p.splits = best_s;
   p.kb_per_split = (p.kb_total + best_s - 1) / best_s;
-  p.partial_bytes = p.splits > 1 ? (size_t)tiles * p.splits * TILE_M * BN * 4 : 0;
   return p;
 }
 
@@ -418,27 +553,34 @@ struct GemmDesc {
   float* db_out;
 };
 
-static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, float* db_partial, TcProblem* P, CUtensorMap* ma,
-                        CUtensorMap* mb) {
+static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, int* counters, float* db_partial, TcProblem* P,
+                        CUtensorMap* ma, CUtensorMap* mb, CUtensorMap* mo) {
   if (!aligned16(d.A) || !aligned16(d.Bm) || d.lda % 8 || d.ldb % 8) return IIF_EALIGN;
   int rc;
   // K-major: memory [MN rows, K cols]; MN-major: memory [K rows, MN cols]
-  rc = d.a_mn ? make_map(ma, d.A, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, 64)
-              : make_map(ma, d.A, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)d.lda, TILE_M);
+  rc = d.a_mn ? make_map(ma, d.A, false, (uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.lda, 64, 64)
+              : make_map(ma, d.A, false, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)d.lda, 64, TILE_M);
   if (rc) return rc;
-  rc = d.b_mn ? make_map(mb, d.Bm, (uint64_t)d.N, (uint64_t)d.K, (uint64_t)d.ldb, 64)
-              : make_map(mb, d.Bm, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)d.ldb, BN);
+  rc = d.b_mn ? make_map(mb, d.Bm, false, (uint64_t)d.N, (uint64_t)d.K, (uint64_t)d.ldb, 64, 64)
+              : make_map(mb, d.Bm, false, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)d.ldb, 64, BN);
   if (rc) return rc;
   *P = TcProblem{};
   P->M = (int)d.M; P->N = (int)d.N; P->K = (int)d.K;
   P->tiles_m = p.tiles_m; P->tiles_n = p.tiles_n; P->kb_total = p.kb_total; P->kb_per_split = p.kb_per_split;
   P->splits = p.splits; P->a_mn = d.a_mn; P->b_mn = d.b_mn;
-  P->alpha = d.alpha; P->bias = d.bias; P->col_scale = d.col_scale; P->bias_vec = d.bias && aligned16(d.bias);
+  P->alpha = d.alpha; P->bias = d.bias; P->col_scale = d.col_scale;
   P->out = d.out; P->out_bf16 = d.out_bf16; P->ldo = d.ldo;
-  P->out_vec = d.out && (d.out_bf16 ? ((reinterpret_cast<uintptr_t>(d.out) & 7u) == 0 && d.ldo % 4 == 0)
-                                    : (aligned16(d.out) && d.ldo % 4 == 0));
-  P->out2 = d.out2; P->ldo2 = d.ldo2; P->out2_vec = d.out2 && aligned16(d.out2) && d.ldo2 % 4 == 0;
-  P->partial = partial;
+  P->out2 = d.out2; P->ldo2 = d.ldo2;
+  // TMA store: one output, 16-byte aligned base and row pitch
+  P->epi_tma = p.splits == 1 && d.out && !d.out2 && aligned16(d.out) && (d.ldo * (d.out_bf16 ? 2 : 4)) % 16 == 0;
+  if (P->epi_tma) {
+    rc = make_map(mo, d.out, !d.out_bf16, (uint64_t)d.N, (uint64_t)d.M, (uint64_t)d.ldo, d.out_bf16 ? 64 : 32, 32);
+    if (rc) return rc;
+  } else {
+    *mo = *ma;
+  }
+  P->partial = reinterpret_cast<float4*>(partial);
+  P->counters = counters;
   P->db_out = d.db_out; P->db_partial = db_partial;
   return IIF_OK;
 }
@@ -447,15 +589,10 @@ static long long* g_dbg = nullptr;   // iif_debug_timing
 
 // Launch one or two problems in one grid.
 static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_bytes_for(MAX_STAGES));
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  const int cap = resident_capacity();
+  if (cap <= 0) { cudaGetLastError(); return IIF_EDRIVER; }
   TcGroup g{};
-  CUtensorMap maps[4] = {};
+  CUtensorMap maps[6] = {};
   Plan plans[2];
   int tiles_total = 0;
   for (int i = 0; i < nprob; ++i) {
@@ -464,71 +601,62 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
   }
   for (int i = 0; i < nprob; ++i) {
     const int mine = (int)(((d[i].M + TILE_M - 1) / TILE_M) * ((d[i].N + BN - 1) / BN));
-    plans[i] = make_plan(d[i].M, d[i].N, d[i].K, nprob > 1 ? tiles_total - mine : 0);
+    plans[i] = make_plan(d[i].M, d[i].N, d[i].K, nprob > 1 ? tiles_total - mine : 0, cap);
   }
-  int cluster = 1;
-  for (int i = 0; i < nprob; ++i) if (plans[i].splits > cluster) cluster = plans[i].splits;
-  // a problem's splits must divide the cluster size so that clusters never straddle tiles unevenly
-  for (int i = 0; i < nprob; ++i)
-    while (cluster % plans[i].splits) {       // fall back to the next smaller exact split count
-      int s = plans[i].splits - 1;
-      for (; s > 1; --s) {
-        const int per = (plans[i].kb_total + s - 1) / s;
-        if ((plans[i].kb_total + per - 1) / per == s && cluster % s == 0) break;
-      }
-      if (s < 1) s = 1;
-      plans[i].splits = s;
-      plans[i].kb_per_split = (plans[i].kb_total + s - 1) / s;
-      const int tiles = plans[i].tiles_m * plans[i].tiles_n;
-      plans[i].partial_bytes = s > 1 ? (size_t)tiles * s * TILE_M * BN * 4 : 0;
+  if (nprob == 2) {   // both plans assumed the other unsplit: keep the sum co-resident, else drop the splits
+    const int total = plans[0].tiles_m * plans[0].tiles_n * plans[0].splits + plans[1].tiles_m * plans[1].tiles_n * plans[1].splits;
+    if ((plans[0].splits > 1 || plans[1].splits > 1) && total > cap) {
+      for (int i = 0; i < 2; ++i)
+        if (plans[i].splits > 1 && plans[1 - i].splits > 1) {   // shrink the one with the smaller K first
+          const int v = plans[0].kb_total < plans[1].kb_total ? 0 : 1;
+          plans[v].splits = 1; plans[v].kb_per_split = plans[v].kb_total;
+          break;
+        }
+      const int t2 = plans[0].tiles_m * plans[0].tiles_n * plans[0].splits + plans[1].tiles_m * plans[1].tiles_n * plans[1].splits;
+      if (t2 > cap)
+        for (int i = 0; i < 2; ++i) { plans[i].splits = 1; plans[i].kb_per_split = plans[i].kb_total; }
     }
+  }
   size_t need = 0;
-  for (int i = 0; i < nprob; ++i) need += plans[i].partial_bytes + (d[i].db_out ? plans[i].db_bytes() : 0);
-  if (need && (!ws || ws_bytes < need)) return IIF_EWORKSPACE;
-  int cta = 0;
-  size_t off = 0;
+  bool any_split = false;
   for (int i = 0; i < nprob; ++i) {
-    float* partial = plans[i].partial_bytes ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + off) : nullptr;
-    off += plans[i].partial_bytes;
+    need += plans[i].partial_bytes() + (d[i].db_out ? plans[i].db_bytes() : 0);
+    any_split |= plans[i].splits > 1;
+  }
+  if (any_split) need += WS_HEADER;
+  if (need && (!ws || ws_bytes < need || !aligned16(ws))) return IIF_EWORKSPACE;
+  int cta = 0;
+  size_t off = WS_HEADER;
+  for (int i = 0; i < nprob; ++i) {
+    float* partial = plans[i].partial_bytes() ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + off) : nullptr;
+    off += plans[i].partial_bytes();
     float* dbp = nullptr;
     if (d[i].db_out && plans[i].db_bytes()) {
       dbp = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + off);
       off += plans[i].db_bytes();
     }
-    int rc = fill_problem(d[i], plans[i], partial, dbp, &g.p[i], &maps[2 * i], &maps[2 * i + 1]);
+    int* counters = any_split ? reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + i * (WS_HEADER / 2)) : nullptr;
+    int rc = fill_problem(d[i], plans[i], partial, counters, dbp, &g.p[i], &maps[2 * i], &maps[2 * i + 1], &maps[4 + i]);
     if (rc) return rc;
     g.cta_begin[i] = cta;
-    int n = plans[i].tiles_m * plans[i].tiles_n * plans[i].splits;
-    n = (n + cluster - 1) / cluster * cluster;          // pad to whole clusters
-    cta += n;
+    cta += plans[i].tiles_m * plans[i].tiles_n * plans[i].splits;
   }
   g.cta_begin[nprob] = cta;
   g.nprob = nprob;
-  g.cluster = cluster;
-  g.stages = MAX_STAGES;
   g.dbg = g_dbg;
-  if (nprob == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
+  if (nprob == 1) { maps[2] = maps[0]; maps[3] = maps[1]; maps[5] = maps[4]; }
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)cta);
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem_bytes_for(g.stages);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attrs[2];
-  int na = 0;
-  attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[na].val.programmaticStreamSerializationAllowed = 1;
-  ++na;
-  if (cluster > 1) {
-    attrs[na].id = cudaLaunchAttributeClusterDimension;
-    attrs[na].val.clusterDim.x = (unsigned)cluster;
-    attrs[na].val.clusterDim.y = 1;
-    attrs[na].val.clusterDim.z = 1;
-    ++na;
-  }
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], g);
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], g);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return (int)e;
   return IIF_OK;
@@ -569,21 +697,10 @@ extern "C" void iif_debug_timing(long long* buf) { g_dbg = buf; }
 
 extern "C" size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C) {
   if (B <= 0 || D <= 0 || C <= 0) return 0;
-  // upper bound: any problem of the head with the largest split count
-  auto cap = [](int64_t M, int64_t N) {
-    return (size_t)((M + TILE_M - 1) / TILE_M) * (size_t)((N + BN - 1) / BN) * MAX_SPLITS * TILE_M * BN * 4;
-  };
-  auto need = [&](int64_t M, int64_t N, int64_t K, int other) {
-    const Plan p = make_plan(M, N, K, other);
-    return p.splits > 1 ? cap(M, N) / MAX_SPLITS * p.splits + p.db_bytes() : (size_t)0;
-  };
-  const int t_dx = (int)(((B + TILE_M - 1) / TILE_M) * ((D + BN - 1) / BN));
-  const int t_dw = (int)(((C + TILE_M - 1) / TILE_M) * ((D + BN - 1) / BN));
-  size_t m = need(B, C, D, 0);
-  size_t t = need(B, D, C, 0); if (t > m) m = t;
-  t = need(C, D, B, 0); if (t > m) m = t;
-  t = need(B, D, C, t_dw) + need(C, D, B, t_dx); if (t > m) m = t;
-  return m;
+  // Upper bound over every launch of the head: split-K never runs more than 2 x 148 CTAs, each
+  // parking one 64 KB partial tile (+ 512 B of db partials), plus the counter header.
+  (void)D;
+  return (size_t)WS_HEADER + (size_t)(2 * kNumSMs) * (TILE_M * BN * 4 + TILE_M * 4);
 }
 
 extern "C" int iif_linear_fwd_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,

@@ -78,7 +78,7 @@ def gemm_workspace(B: int, D: int, Cc: int, device) -> Optional[torch.Tensor]:
     key = (torch.device(device).index or 0, torch.cuda.current_stream(device).cuda_stream)
     t = _WS.get(key)
     if t is None or t.numel() < n:
-        t = torch.empty(n, dtype=torch.uint8, device=device)
+        t = torch.zeros(n, dtype=torch.uint8, device=device)   # split-K counters start (and stay) zero
         _WS[key] = t
     return t
 
@@ -382,7 +382,7 @@ class HeadStep:
         n = int(_lib.load().iif_gemm_ws_bytes(B, D, Cc))
         if ws is not None and ws.numel() < n:
             raise ValueError("HeadStep: shared workspace too small")
-        self.ws = ws if ws is not None else torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        self.ws = ws if ws is not None else torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
         self.ws_bytes = n
         self.dx_dtype = _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32
         self.launches_per_step = 3

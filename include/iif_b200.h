@@ -162,8 +162,11 @@ IIF_API int iif_colsum(const void* dz, int dz_dtype, int64_t lddz, const float* 
 /* ---------------------------------------------------------------------------------------------
  * (a)/(c) fc_cls GEMMs.  *_bf16: tcgen05.mma (TMEM accumulators, TMA-fed), bf16 operands, fp32
  * accumulation.  *_f32: FFMA, fp32 operands (the 1e-5 parity mode).
- * `ws`: workspace of at least iif_gemm_ws_bytes(...) bytes (split-K partial tiles exchanged inside a
- * thread-block cluster; contents need no initialisation); may be NULL when iif_gemm_ws_bytes returns 0.
+ * `ws`: 16-byte aligned workspace of at least iif_gemm_ws_bytes(...) bytes: a 4 KB header of split-K
+ * arrival counters followed by the fp32 partial tiles.  The HEADER MUST BE ZERO when the workspace is
+ * first used (cudaMemset it once at allocation); every launch leaves it zero again, so one workspace
+ * serves any number of stream-ordered launches.  One workspace per stream (not re-entrant across
+ * streams).
  * bf16 alignment: base pointers 16 bytes; leading dimensions of bf16 operands multiples of 8.
  * ------------------------------------------------------------------------------------------- */
 

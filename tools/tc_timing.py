@@ -8,8 +8,8 @@ dev = "cuda:0"
 B, D, C = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256,2048,1000").split(","))
 lib = _lib.load()
 bf = torch.bfloat16
-NAMES = ["start", "prologue", "griddep", "tma_issued", "first_full", "last_full", "acc_done", "staged",
-         "partial_out", "cluster", "end"]
+NAMES = ["start", "prologue", "griddep", "tma_issued", "first_full", "last_full", "acc_done", "partial_out",
+         "rendezvous", "end"]
 
 def show(tag, fn, n_cta_max=4096):
     buf = torch.zeros(n_cta_max * 16, dtype=torch.int64, device=dev)
@@ -25,7 +25,7 @@ def show(tag, fn, n_cta_max=4096):
     t = buf.cpu().numpy().reshape(-1, 16)
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
-    print(f"== {tag}: {len(t)} CTAs, kernel span {(t[:, :11].max() - t0) / 1e3:.2f} us")
+    print(f"== {tag}: {len(t)} CTAs, kernel span {(t[:, :10].max() - t0) / 1e3:.2f} us")
     for i, n in enumerate(NAMES):
         col = t[:, i]
         col = col[col > 0]
