@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--variant", default="smooth")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused-loss", action="store_true", help="3 launches per step (loss rows in their own launch)")
+    ap.add_argument("--no-prefetch", action="store_true", help="do not request x / w tiles before the dependency wait")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--sync-allreduce", action="store_true", help="N>1: all-reduce on the compute stream (no overlap)")
     return ap.parse_args()
@@ -182,7 +184,8 @@ def main():
         w = ((torch.rand(C, D, generator=g) * 2 - 1) / D ** 0.5).to(dev).to(torch.bfloat16)
         y = torch.multinomial(prob, B, replacement=True, generator=g).to(dev)
         bias = torch.full((C,), 0.01, device=dev)
-        hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws)
+        hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws,
+                          fused_loss=not args.no_fused_loss, stable_operands=not args.no_prefetch)
         hs.bind(x, w, bias, iif, y)
         sets.append(hs)
     launches_per_step = sets[0].launches_per_step
@@ -258,43 +261,48 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
     loss_val = float(sets[(args.steps - 1) % S].loss)
 
-    # ---- e2e: public API call with HOST (pinned) inputs; H2D of x,y and D2H of the loss every step
+    # ---- e2e: the public host-batch API (ops.HeadPipeline -> iif_pipeline_*): every step copies its
+    # features + labels from PINNED HOST memory, runs the head step and copies the loss back to the
+    # host; the loop reads each step's loss with a lag of `lag` steps (asynchronous logging), so the
+    # next batch's PCIe copy overlaps the current step's kernels.  Wall clock, synchronised both sides.
     hx = [torch.randn(B, D, generator=g).to(torch.bfloat16).pin_memory() for _ in range(4)]
     hy = [torch.multinomial(prob, B, replacement=True, generator=g).pin_memory() for _ in range(4)]
-    hloss = torch.zeros((), dtype=torch.float32).pin_memory()
-    xs = [hs._keep[0] for hs in sets]
-    ys = [hs._keep[4] for hs in sets]
+    pipe = ops.HeadPipeline(sets)
+    lag = 4
+    e2e_loss = [0.0]
 
-    def e2e_step(i):
-        k = i % S
-        xs[k].copy_(hx[i % 4], non_blocking=True)
-        ys[k].copy_(hy[i % 4], non_blocking=True)
-        step(i)
-        hloss.copy_(sets[k].loss, non_blocking=True)
-        cur.synchronize()
-        return float(hloss)
+    def e2e_run(n):
+        for i in range(n):
+            k = i % S
+            if i >= lag:
+                e2e_loss[0] = pipe.wait((i - lag) % S)          # device -> host read of step i-lag's loss
+            pipe.submit(k, hx[i % 4], hy[i % 4])
+            if world > 1:
+                pipe.stream_wait_step(k, comm)
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
+                pipe.hold_slot(k, comm)
+        for i in range(max(n - lag, 0), n):
+            e2e_loss[0] = pipe.wait(i % S)
+        pipe.sync()
+        if world > 1:
+            comm.synchronize()
 
     n_e2e = min(args.steps, 3000)
-    for i in range(10):
-        e2e_step(i)
+    e2e_run(32)
     fence()
     t0 = time.perf_counter()
-    e0.record(cur)
-    for i in range(n_e2e):
-        e2e_step(i)
-    if world > 1:
-        cur.wait_stream(comm)
-    e1.record(cur)
+    e2e_run(n_e2e)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
     fence()
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e2e_ms, wall_ms)      # host-synchronised loop: wall clock and events agree; keep the larger
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e = {"value": world * B * n_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * D * 2 + B * 8,
-           "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e}
+           "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e, "loss_read_lag_steps": lag,
+           "api": "iif_b200.ops.HeadPipeline (iif_pipeline_submit / iif_pipeline_wait)", "last_loss": e2e_loss[0]}
+    pipe.close()
 
     # ---- per-kernel timing (rank 0): each kernel of the step alone, back to back over the rotating sets
     pk = peaks()
@@ -305,6 +313,9 @@ def main():
             "linear_fwd_bf16": (e * (B * D + C * D) + 4 * B * C + 4 * C, 2.0 * B * D * C),
             "softmax_ce_fwd_bwd": (4 * B * C + 2 * B * C + 8 * B + 8 * B + 4 * C, 0.0),
             "linear_bwd_bf16": (2 * B * C + e * C * D + e * B * D + e * B * D + 4 * C * D + 4 * C, 4.0 * B * D * C),
+            # loss rows + dX + dW + db in one launch: Z in, dZ out (its re-read comes from L2), X, W in, dX, dW, db out
+            "loss_linear_bwd_bf16": (4 * B * C + 2 * B * C + 16 * B + 4 * C + e * C * D + e * B * D + e * B * D
+                                     + 4 * C * D + 4 * C, 4.0 * B * D * C),
         }
         names = [n for n, _ in sets[0].kernels()]
         reps = max(1, 1200 // S)
@@ -359,7 +370,8 @@ def main():
                            "parallelism": f"dp{world} (row sharding, NCCL all-reduce(mean) of dW+db "
                                           f"{'on the compute stream' if args.sync_allreduce else 'overlapped on a side stream'})"
                                           if world > 1 else "dp1",
-                           "launch": "cuda-graph replay (one graph per step)" if use_graph else "eager",
+                           "launch": (f"cuda-graph replay (one graph = the {launches_per_step} launches of a step)"
+                                      if use_graph else "eager"),
                            "l2": f"rotating {S} independent input+output sets, {S * per_set / 1e6:.0f} MB > 126 MB L2"},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
                 "kernels": kern, "cpu_baseline": cpu, "loss": loss_val}

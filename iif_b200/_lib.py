@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libiif_b200.so")
 OK, EINVAL, EALIGN, EUNSUPPORTED, EWORKSPACE, EDRIVER = 0, -1, -2, -3, -4, -5
 VARIANT_IDS = {"raw": 0, "smooth": 1, "rel": 2, "prob": 2, "normit": 3, "gombit": 4, "base2": 5, "base10": 6}
 DTYPE_F32, DTYPE_BF16 = 0, 1
+HEAD_NO_FUSED_LOSS = 1
+HEAD_STABLE_OPERANDS = 2
 
 _p, _i64, _i32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t
 
@@ -26,7 +28,7 @@ class HeadArgs(C.Structure):
         ("B", _i64), ("D", _i64), ("C", _i64),
         ("z", _p), ("ldz", _i64), ("loss_i", _p), ("loss_sum", _p), ("dz_bf16", _p), ("lddz", _i64),
         ("dx", _p), ("dx_dtype", _i32), ("lddx", _i64), ("dw", _p), ("lddw", _i64), ("db", _p),
-        ("argmax", _p), ("rank", _p), ("acc_counts", _p), ("scratch", _p), ("ws", _p), ("ws_bytes", _sz),
+        ("argmax", _p), ("rank", _p), ("acc_counts", _p), ("scratch", _p), ("ws", _p), ("ws_bytes", _sz), ("flags", _i32),
     ]
 
 
@@ -56,8 +58,18 @@ SIGNATURES = {
     "iif_linear_bwd_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _i64, _i64, _p,
                                    _sz, _p]),
     "iif_debug_timing": (None, [_p]),
+    "iif_debug_capacity": (_i32, [_p]),
+    "iif_pipeline_create": (_i32, [C.POINTER(_p), C.POINTER(HeadArgs), _i32]),
+    "iif_pipeline_submit": (_i32, [_p, _i32, _p, _p, _p]),
+    "iif_pipeline_wait": (_i32, [_p, _i32]),
+    "iif_pipeline_stream_wait_step": (_i32, [_p, _i32, _p]),
+    "iif_pipeline_hold_slot": (_i32, [_p, _i32, _p]),
+    "iif_pipeline_sync": (_i32, [_p]),
+    "iif_pipeline_destroy": (None, [_p]),
     "iif_gemm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "iif_head_fwd_bwd_bf16": (_i32, [C.POINTER(HeadArgs), _p]),
+    "iif_loss_linear_bwd_bf16": (_i32, [C.POINTER(HeadArgs), _p]),
+    "iif_head_launches": (_i32, [C.POINTER(HeadArgs)]),
 }
 
 _lib = None

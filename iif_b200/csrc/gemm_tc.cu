@@ -51,6 +51,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "loss_row.cuh"
 #include "ptx.cuh"
 
 namespace iif {
@@ -68,8 +69,12 @@ constexpr int TMEM_COLS = 256;        // BN accumulator columns + 16 for db (pow
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + BAR_BYTES + 2 * BN * 4 + 1024;
 constexpr int GEN_PITCH = 65;         // generic epilogue: warp-private 32 x 65 float slab
-constexpr int WS_HEADER = 4096;       // split-K counters: 2 problems x 256 tiles x {arrive, done}
+constexpr int WS_HEADER = 8192;       // split-K counters: 2 problems x 256 tiles x {arrive, done}; grid barrier at 4096
 constexpr int TILE_F4 = TILE_M * BN / 4;
+// Split-K arrival counters never reset: every CTA of a tile adds EPOCH_UNIT / splits, so each launch
+// advances the tile's counter by exactly EPOCH_UNIT whatever its split count (840 = lcm(1..8)); the
+// value an arriver gets back tells it which multiple to wait for.  64-bit: no wrap in practice.
+constexpr unsigned long long EPOCH_UNIT = 840;
 static_assert(8 * 32 * GEN_PITCH * 4 <= STAGES * STAGE_BYTES, "generic staging must fit in the stage ring");
 static_assert(TILE_M * BN * 4 <= STAGES * STAGE_BYTES, "TMA-store staging must fit in the stage ring");
 
@@ -81,7 +86,9 @@ struct TcProblem {
   void* out; int out_bf16; int64_t ldo; int epi_tma;
   float* out2; int64_t ldo2;
   float4* partial;                                  // [tiles][splits][TILE_F4] fp32x4, layout part_idx()
-  int* counters;                                    // [tiles][2]: arrive, done (zero between launches)
+  unsigned long long* counters;                     // [tiles] arrival epochs (see EPOCH_UNIT)
+  int pre_a, pre_b;                                 // operand not written by the preceding kernel: may be
+                                                    // requested before the programmatic-dependency wait
   float* db_out; float* db_partial;                 // dW only: db[m] (and [tiles_m][splits][TILE_M] partials)
 };
 
@@ -90,6 +97,11 @@ struct TcGroup {
   int cta_begin[3];
   long long* dbg;                        // optional per-CTA phase timestamps (iif_debug_timing)
   TcProblem p[2];
+  // loss-fused backward launch: every CTA first runs rows of the IIF softmax-CE (loss_row.cuh) that
+  // PRODUCES the A operand (dZ), the grid meets at `grid_bar`, then the GEMMs consume dZ from L2.
+  int fuse_loss, loss_ne;
+  int* grid_bar;                         // arrival count, zero between launches
+  RowArgs loss;
 };
 
 __device__ __forceinline__ void stamp(const TcGroup& g, int slot) {
@@ -175,7 +187,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (P.epi_tma) ptx::prefetch_tensormap(tmO);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    // full barriers take TWO producer arrivals per phase (B part, A part): the B operand of a loss-fused
+    // launch is requested before the loss rows run, the A operand (dZ) only after the grid barrier
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(full_bar(s), 2); ptx::mbar_init(empty_bar(s), 1); }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
@@ -195,9 +209,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_p;
 
   if (threadIdx.x == 0) stamp(g, 1);
+  const int n_first = min(STAGES, kb_end - kb_begin);       // k-blocks that fit the ring without recycling
+  auto load_b = [&](int stage, int kb) {
+    const uint32_t sb = smem_base + stage * STAGE_BYTES + A_STAGE_BYTES;
+    ptx::mbar_arrive_expect_tx(full_bar(stage), B_STAGE_BYTES);
+    const int k0 = kb * TILE_K;
+    if (P.b_mn) {
+#pragma unroll
+      for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, tmB, full_bar(stage), n0 + 64 * j, k0);
+    } else {
+      ptx::tma_load_2d(sb, tmB, full_bar(stage), k0, n0);
+    }
+  };
+  auto load_a = [&](int stage, int kb) {
+    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+    ptx::mbar_arrive_expect_tx(full_bar(stage), A_STAGE_BYTES);
+    const int k0 = kb * TILE_K;
+    if (P.a_mn) {
+#pragma unroll
+      for (int j = 0; j < TILE_M / 64; ++j) ptx::tma_load_2d(sa + j * 8192, tmA, full_bar(stage), m0 + 64 * j, k0);
+    } else {
+      ptx::tma_load_2d(sa, tmA, full_bar(stage), k0, m0);
+    }
+  };
+  // Operands the preceding kernel of the stream does not write (caller's promise) are requested BEFORE the
+  // dependency wait: their HBM latency hides under the predecessor's tail.
+  const int early_a = (P.pre_a && !g.fuse_loss) ? n_first : 0;
+  const int early_b = (P.pre_b || g.fuse_loss) ? n_first : 0;
+  if (threadIdx.x == 0) {
+    if (P.pre_b) for (int i = 0; i < n_first; ++i) load_b(i, kb_begin + i);
+    for (int i = 0; i < early_a; ++i) load_a(i, kb_begin + i);
+  }
   ptx::griddep_launch_dependents();      // the next kernel may start its own prologue now
   ptx::griddep_wait();                   // ... and ours ends here: the producer kernel's data is visible
   if (threadIdx.x == 0) stamp(g, 2);
+
+  double loss_part = 0.0;
+  int loss_c1 = 0, loss_c5 = 0;
+  if (g.fuse_loss) {
+    // ---- loss-fused launch: B operands (X / W tiles: independent of the loss) are requested first ...
+    if (threadIdx.x == 0 && !P.pre_b)
+      for (int i = 0; i < n_first; ++i) load_b(i, kb_begin + i);
+    // ---- ... then every CTA computes its share of the loss rows: Z -> loss_i, dZ (bf16, global)
+    __shared__ RowSmem<256> row_sm;
+    for (int64_t r = blockIdx.x; r < g.loss.B; r += gridDim.x) {
+      float my_loss; int cnt; bool active;
+      if (g.loss_ne == 4) softmax_row_body<256, 4, true, 0>(g.loss, r, row_sm, my_loss, cnt, active);
+      else if (g.loss_ne == 8) softmax_row_body<256, 8, true, 0>(g.loss, r, row_sm, my_loss, cnt, active);
+      else softmax_row_body<256, 16, true, 0>(g.loss, r, row_sm, my_loss, cnt, active);
+      if (threadIdx.x == 0) { loss_part += (double)my_loss; loss_c1 += cnt < 1; loss_c5 += cnt < 5; }
+      __syncthreads();
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");   // our dZ stores (generic proxy) vs. the TMA reads to come
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      stamp(g, 10);
+      __threadfence();
+      ptx::red_release_add(g.grid_bar, 1);
+      ptx::spin_until_ge(g.grid_bar, (int)gridDim.x);   // every row of dZ is in L2
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      stamp(g, 11);
+    }
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -205,21 +279,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-        const int k0 = kb * TILE_K;
-        if (P.a_mn) {
-#pragma unroll
-          for (int j = 0; j < TILE_M / 64; ++j) ptx::tma_load_2d(sa + j * 8192, tmA, full_bar(stage), m0 + 64 * j, k0);
-        } else {
-          ptx::tma_load_2d(sa, tmA, full_bar(stage), k0, m0);
-        }
-        if (P.b_mn) {
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, tmB, full_bar(stage), n0 + 64 * j, k0);
-        } else {
-          ptx::tma_load_2d(sb, tmB, full_bar(stage), k0, n0);
-        }
+        if (kb - kb_begin >= early_b) load_b(stage, kb);
+        if (kb - kb_begin >= early_a) load_a(stage, kb);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       stamp(g, 3);                       // all TMA loads issued
@@ -376,31 +437,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::tmem_ld_wait();
       __stcg(dbp + split * TILE_M + row, __uint_as_float(v));
     }
-    int* arrive = P.counters + 2 * tile;
+    unsigned long long* arrive = P.counters + tile;
     __syncthreads();                         // every thread's partial stores are issued ...
     if (threadIdx.x == 0) {
       stamp(g, 7);
       __threadfence();                       // ... and made visible at gpu scope (cumulative) before the arrival
-      ptx::red_release_add(arrive, 1);
-      ptx::spin_until_ge(arrive, P.splits);
+      const unsigned long long inc = EPOCH_UNIT / (unsigned)P.splits;
+      const unsigned long long old = ptx::atom_add_release_u64(arrive, inc);
+      const unsigned long long target = (old / EPOCH_UNIT + 1) * EPOCH_UNIT;
+      if (old + inc < target) ptx::spin_until_ge_u64(arrive, target);
       __threadfence();
       stamp(g, 8);
     }
     __syncthreads();
     const int gps = (TILE_M / 8 + P.splits - 1) / P.splits;          // 8-row groups per split
     const int g0 = split * gps, g1 = min(TILE_M / 8, g0 + gps);
-    for (int grp = g0; grp < g1; ++grp) {
+    for (int grp = g0; grp < g1; grp += 2) {                          // two groups per pass: 2 x splits loads in flight
+      const bool two = grp + 1 < g1;
       const int idx = grp * 256 + threadIdx.x;
-      float4 t[MAX_SPLITS];
+      float4 t[2][MAX_SPLITS];
 #pragma unroll
       for (int s = 0; s < MAX_SPLITS; ++s)
-        if (s < P.splits) t[s] = __ldcg(base + (int64_t)s * TILE_F4 + idx);
-      float4 acc = t[0];
+        if (s < P.splits) {
+          t[0][s] = __ldcg(base + (int64_t)s * TILE_F4 + idx);
+          if (two) t[1][s] = __ldcg(base + (int64_t)s * TILE_F4 + idx + 256);
+        }
 #pragma unroll
-      for (int s = 1; s < MAX_SPLITS; ++s)   // fixed split order: deterministic sum
-        if (s < P.splits) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }
-      const int j = threadIdx.x >> 3;
-      emit4(P, m0 + grp * 8 + (threadIdx.x & 7), n0 + 4 * j, acc, alpha, s_bias, s_scale, 4 * j);
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        float4 acc = t[u][0];
+#pragma unroll
+        for (int s = 1; s < MAX_SPLITS; ++s)   // fixed split order: deterministic sum
+          if (s < P.splits) { acc.x += t[u][s].x; acc.y += t[u][s].y; acc.z += t[u][s].z; acc.w += t[u][s].w; }
+        const int j = threadIdx.x >> 3;
+        emit4(P, m0 + (grp + u) * 8 + (threadIdx.x & 7), n0 + 4 * j, acc, alpha, s_bias, s_scale, 4 * j);
+      }
     }
     if (do_db) {
       const int r0 = g0 * 8, r1 = g1 * 8;
@@ -409,11 +480,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < P.splits; ++s) acc += __ldcg(dbp + s * TILE_M + r0 + threadIdx.x);
         P.db_out[m0 + r0 + threadIdx.x] = acc * alpha;
       }
-    }
-    __syncthreads();                         // all reads of the partials done
-    if (threadIdx.x == 0 && atomicAdd(arrive + 1, 1) == P.splits - 1) {   // last reader re-arms the counters
-      arrive[0] = 0;
-      arrive[1] = 0;
     }
   }
   ptx::tc_fence_before();
@@ -424,6 +490,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
   if (threadIdx.x == 0) stamp(g, 9);
+  if (g.fuse_loss) {
+    // off the GEMMs' critical path: deterministic loss sum / top-k counts, then re-arm the grid barrier
+    // (the ticket of the tail doubles as the "everyone is past the grid barrier" count: its last CTA re-arms it)
+    if (grid_tail<256>(loss_part, loss_c1, loss_c5, g.loss.loss_sum, g.loss.acc_counts, g.loss.scratch) && threadIdx.x == 0)
+      *g.grid_bar = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,20 +564,39 @@ static int make_map(CUtensorMap* out, const void* ptr, bool f32, uint64_t inner,
 
 // Resident-CTA capacity of the device for this kernel (2 per SM on B200): the split-K rendezvous
 // needs every CTA of the grid on an SM at the same time.
-static int resident_capacity() {
+static int resident_capacity(int* detail = nullptr) {
   static std::mutex mu;
   static int caps[64] = {};              // per device ordinal; 0 = not yet queried
+  static int details[64][6] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
   std::lock_guard<std::mutex> g(mu);
   if (caps[dev] == 0) {
-    int sms = 0, per = 0;
+    int sms = 0, per_api = 0, smem_sm = 0, regs_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
     if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
       return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, gemm_tc_kernel, 256, SMEM_BYTES) != cudaSuccess) return 0;
+    // two ~100 KB CTAs per SM need the full shared-memory carve-out (the default sizes it for one)
+    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_api, gemm_tc_kernel, 256, SMEM_BYTES);
+    // Own bound from the hardware limits (shared memory incl. 1 KB/CTA reserved, registers in 8-register
+    // warp granules, 512 TMEM columns); the runtime's occupancy answer is taken when it is larger.
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, gemm_tc_kernel) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    const int by_smem = smem_sm / (SMEM_BYTES + 1024 + (int)fa.sharedSizeBytes);
+    const int by_regs = regs_sm / (((fa.numRegs + 7) / 8 * 8) * 256);
+    int per = by_smem < by_regs ? by_smem : by_regs;
+    if (per > 512 / TMEM_COLS) per = 512 / TMEM_COLS;
+    if (per_api > per) per = per_api;
+    if (per < 1) per = 1;
     caps[dev] = sms * per;
+    const int d[6] = {per_api, by_smem, by_regs, fa.numRegs, smem_sm, (int)fa.sharedSizeBytes};
+    for (int i = 0; i < 6; ++i) details[dev][i] = d[i];
+    cudaGetLastError();
   }
+  if (detail) for (int i = 0; i < 6; ++i) detail[i] = details[dev][i];
   return caps[dev];
 }
 
@@ -551,9 +642,11 @@ struct GemmDesc {
   void* out; int out_bf16; int64_t ldo;
   float* out2; int64_t ldo2;
   float* db_out;
+  int pre_a, pre_b;
 };
 
-static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, int* counters, float* db_partial, TcProblem* P,
+static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, unsigned long long* counters, float* db_partial,
+                        TcProblem* P,
                         CUtensorMap* ma, CUtensorMap* mb, CUtensorMap* mo) {
   if (!aligned16(d.A) || !aligned16(d.Bm) || d.lda % 8 || d.ldb % 8) return IIF_EALIGN;
   int rc;
@@ -581,6 +674,7 @@ static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, int* c
   }
   P->partial = reinterpret_cast<float4*>(partial);
   P->counters = counters;
+  P->pre_a = d.pre_a; P->pre_b = d.pre_b;
   P->db_out = d.db_out; P->db_partial = db_partial;
   return IIF_OK;
 }
@@ -588,7 +682,8 @@ static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, int* c
 static long long* g_dbg = nullptr;   // iif_debug_timing
 
 // Launch one or two problems in one grid.
-static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes, cudaStream_t st,
+                        const RowArgs* loss = nullptr, bool dry_run = false) {
   const int cap = resident_capacity();
   if (cap <= 0) { cudaGetLastError(); return IIF_EDRIVER; }
   TcGroup g{};
@@ -623,7 +718,7 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
     need += plans[i].partial_bytes() + (d[i].db_out ? plans[i].db_bytes() : 0);
     any_split |= plans[i].splits > 1;
   }
-  if (any_split) need += WS_HEADER;
+  if (any_split || loss) need += WS_HEADER;
   if (need && (!ws || ws_bytes < need || !aligned16(ws))) return IIF_EWORKSPACE;
   int cta = 0;
   size_t off = WS_HEADER;
@@ -635,7 +730,8 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
       dbp = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + off);
       off += plans[i].db_bytes();
     }
-    int* counters = any_split ? reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + i * (WS_HEADER / 2)) : nullptr;
+    unsigned long long* counters =
+        any_split ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + i * 2048) : nullptr;
     int rc = fill_problem(d[i], plans[i], partial, counters, dbp, &g.p[i], &maps[2 * i], &maps[2 * i + 1], &maps[4 + i]);
     if (rc) return rc;
     g.cta_begin[i] = cta;
@@ -644,8 +740,17 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
   g.cta_begin[nprob] = cta;
   g.nprob = nprob;
   g.dbg = g_dbg;
+  if (loss) {
+    // the grid barrier needs every CTA resident; C <= 4096 with 256 threads per row
+    if (cta > cap || loss->C > 4096 || (loss->C & 3) || !loss->scratch) return IIF_EUNSUPPORTED;
+    g.fuse_loss = 1;
+    g.loss_ne = loss->C <= 1024 ? 4 : (loss->C <= 2048 ? 8 : 16);
+    g.grid_bar = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + 4096);
+    g.loss = *loss;
+  }
   if (nprob == 1) { maps[2] = maps[0]; maps[3] = maps[1]; maps[5] = maps[4]; }
 
+  if (dry_run) return IIF_OK;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)cta);
   cfg.blockDim = dim3(256);
@@ -666,23 +771,28 @@ static bool bad_dims(int64_t B, int64_t D, int64_t C) {
   return B < 0 || D <= 0 || C <= 0 || B > INT32_MAX || D > INT32_MAX || C > INT32_MAX;
 }
 
+// `stable`: X and W are not written by the launch preceding this one on the stream (see IIF_HEAD_STABLE_OPERANDS)
 static GemmDesc desc_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* cs,
-                         float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B, int64_t D, int64_t C) {
+                         float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B, int64_t D, int64_t C,
+                         bool stable = false) {
   GemmDesc d{};
+  d.pre_a = d.pre_b = stable;
   d.A = x; d.lda = ldx; d.a_mn = false; d.Bm = w; d.ldb = ldw; d.b_mn = false; d.M = B; d.N = C; d.K = D;
   d.bias = bias; d.col_scale = cs; d.out = z; d.out_bf16 = 0; d.ldo = ldz; d.out2 = zs; d.ldo2 = ldzs;
   return d;
 }
 static GemmDesc desc_dx(const void* dz, int64_t lddz, const void* w, int64_t ldw, const float* alpha, void* dx,
-                        int dx_bf16, int64_t lddx, int64_t B, int64_t D, int64_t C) {
+                        int dx_bf16, int64_t lddx, int64_t B, int64_t D, int64_t C, bool stable = false) {
   GemmDesc d{};
+  d.pre_b = stable;
   d.A = dz; d.lda = lddz; d.a_mn = false; d.Bm = w; d.ldb = ldw; d.b_mn = true; d.M = B; d.N = D; d.K = C;
   d.alpha = alpha; d.out = dx; d.out_bf16 = dx_bf16; d.ldo = lddx;
   return d;
 }
 static GemmDesc desc_dw(const void* dz, int64_t lddz, const void* x, int64_t ldx, const float* alpha, float* dw,
-                        int64_t lddw, int64_t B, int64_t D, int64_t C, float* db_out) {
+                        int64_t lddw, int64_t B, int64_t D, int64_t C, float* db_out, bool stable = false) {
   GemmDesc d{};
+  d.pre_b = stable;
   d.A = dz; d.lda = lddz; d.a_mn = true; d.Bm = x; d.ldb = ldx; d.b_mn = true; d.M = C; d.N = D; d.K = B;
   d.alpha = alpha; d.out = dw; d.out_bf16 = 0; d.ldo = lddw;
   d.db_out = db_out;
@@ -694,6 +804,7 @@ static GemmDesc desc_dw(const void* dz, int64_t lddz, const void* x, int64_t ldx
 using namespace iif;
 
 extern "C" void iif_debug_timing(long long* buf) { g_dbg = buf; }
+extern "C" int iif_debug_capacity(int* detail6) { return resident_capacity(detail6); }
 
 extern "C" size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C) {
   if (B <= 0 || D <= 0 || C <= 0) return 0;
@@ -703,14 +814,22 @@ extern "C" size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C) {
   return (size_t)WS_HEADER + (size_t)(2 * kNumSMs) * (TILE_M * BN * 4 + TILE_M * 4);
 }
 
-extern "C" int iif_linear_fwd_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
-                                   const float* col_scale, float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B,
-                                   int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream) {
+namespace iif {
+int linear_fwd_bf16_ex(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* col_scale,
+                       float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B, int64_t D, int64_t C, void* ws,
+                       size_t ws_bytes, void* stream, bool stable) {
   if (bad_dims(B, D, C) || !w || (B > 0 && !x) || (!z && !zs) || ldx < D || ldw < D) return IIF_EINVAL;
   if ((z && ldz < C) || (zs && (ldzs < C || !col_scale))) return IIF_EINVAL;
   if (B == 0) return IIF_OK;
-  const GemmDesc d = desc_fwd(x, ldx, w, ldw, bias, col_scale, z, ldz, zs, ldzs, B, D, C);
+  const GemmDesc d = desc_fwd(x, ldx, w, ldw, bias, col_scale, z, ldz, zs, ldzs, B, D, C, stable);
   return launch_group(&d, 1, ws, ws_bytes, (cudaStream_t)stream);
+}
+}  // namespace iif
+
+extern "C" int iif_linear_fwd_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
+                                   const float* col_scale, float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B,
+                                   int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream) {
+  return linear_fwd_bf16_ex(x, ldx, w, ldw, bias, col_scale, z, ldz, zs, ldzs, B, D, C, ws, ws_bytes, stream, false);
 }
 
 extern "C" int iif_linear_bwd_dx_bf16(const void* dz, int64_t lddz, const void* w, int64_t ldw, const float* alpha_dev,
@@ -735,10 +854,10 @@ extern "C" int iif_linear_bwd_dw_bf16(const void* dz, int64_t lddz, const void* 
   return launch_group(&d, 1, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
-                                   const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw,
-                                   int64_t lddw, float* db, int64_t B, int64_t D, int64_t C, void* ws,
-                                   size_t ws_bytes, void* stream) {
+namespace iif {
+int linear_bwd_bf16_ex(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
+                       const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw, int64_t lddw, float* db,
+                       int64_t B, int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream, bool stable) {
   if (bad_dims(B, D, C) || !dw || (B > 0 && (!dz || !x)) || lddz < C || ldx < D || lddw < D) return IIF_EINVAL;
   if (dx && (!w || ldw < D || lddx < D || (dx_dtype != IIF_DTYPE_F32 && dx_dtype != IIF_DTYPE_BF16))) return IIF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -749,7 +868,50 @@ extern "C" int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, 
   }
   GemmDesc d[2];
   int n = 0;
-  if (dx) d[n++] = desc_dx(dz, lddz, w, ldw, alpha_dev, dx, dx_dtype == IIF_DTYPE_BF16, lddx, B, D, C);
-  d[n++] = desc_dw(dz, lddz, x, ldx, alpha_dev, dw, lddw, B, D, C, db);
+  if (dx) d[n++] = desc_dx(dz, lddz, w, ldw, alpha_dev, dx, dx_dtype == IIF_DTYPE_BF16, lddx, B, D, C, stable);
+  d[n++] = desc_dw(dz, lddz, x, ldx, alpha_dev, dw, lddw, B, D, C, db, stable);
   return launch_group(d, n, ws, ws_bytes, st);
+}
+}  // namespace iif
+
+extern "C" int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
+                                   const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw,
+                                   int64_t lddw, float* db, int64_t B, int64_t D, int64_t C, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  return linear_bwd_bf16_ex(dz, lddz, x, ldx, w, ldw, alpha_dev, dx, dx_dtype, lddx, dw, lddw, db, B, D, C, ws, ws_bytes,
+                            stream, false);
+}
+
+static int loss_linear_bwd(const iif_head_args* h, void* stream, bool dry_run) {
+  if (!h || !h->x || !h->label || !h->z || !h->dz_bf16 || !h->dw) return IIF_EINVAL;
+  const int64_t B = h->B, D = h->D, C = h->C;
+  if (bad_dims(B, D, C) || B == 0 || h->lddz % 8 != 0 || h->lddz < C || h->ldz < C || h->ldx < D || h->lddw < D)
+    return B == 0 ? IIF_EUNSUPPORTED : IIF_EINVAL;
+  if (h->dx && (!h->w || h->ldw < D || h->lddx < D)) return IIF_EINVAL;
+  if ((h->loss_sum || h->acc_counts) && !h->scratch) return IIF_EINVAL;
+  if (h->acc_counts && !h->rank) return IIF_EINVAL;
+  RowArgs a;
+  const bool vec = make_ce_row_args(a, h->z, h->ldz, h->iif, h->label, h->class_weight, h->sample_weight, h->ignore_index,
+                                    h->scale, B, C, h->loss_i, h->loss_sum, nullptr, 0, h->dz_bf16, h->lddz, nullptr,
+                                    h->argmax, h->rank, h->acc_counts, h->scratch);
+  if (!vec) return IIF_EUNSUPPORTED;
+  GemmDesc d[2];
+  int n = 0;
+  const bool stable = (h->flags & IIF_HEAD_STABLE_OPERANDS) != 0;
+  if (h->dx)
+    d[n++] = desc_dx(h->dz_bf16, h->lddz, h->w, h->ldw, nullptr, h->dx, h->dx_dtype == IIF_DTYPE_BF16, h->lddx, B, D, C, stable);
+  d[n++] = desc_dw(h->dz_bf16, h->lddz, h->x, h->ldx, nullptr, h->dw, h->lddw, B, D, C, h->db, stable);
+  return launch_group(d, n, h->ws, h->ws_bytes, (cudaStream_t)stream, &a, dry_run);
+}
+
+extern "C" int iif_loss_linear_bwd_bf16(const iif_head_args* h, void* stream) { return loss_linear_bwd(h, stream, false); }
+
+// Launches iif_head_fwd_bwd_bf16 will make for these arguments: 2 (loss rows fused into the backward
+// launch) or 3; negative = argument error.
+extern "C" int iif_head_launches(const iif_head_args* h) {
+  if (!h) return IIF_EINVAL;
+  if (h->flags & IIF_HEAD_NO_FUSED_LOSS) return 3;
+  const int rc = loss_linear_bwd(h, nullptr, true);
+  if (rc == IIF_OK) return 2;
+  return rc == IIF_EUNSUPPORTED ? 3 : rc;
 }

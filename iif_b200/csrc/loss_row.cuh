@@ -1,0 +1,338 @@
+// Row kernels of the fused IIF softmax-CE (shared by loss.cu and the loss-fused backward GEMM launch of
+// gemm_tc.cu).  Reference semantics restated (never copied): cls/custom.py:28-39;
+// seg/mmdet/models/losses/iif_loss.py:65-78,187-200; losses/utils.py:28-55; losses/accuracy.py:41-50.
+#pragma once
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace iif {
+
+struct RowArgs {
+  const float* z; int64_t ldz;
+  const float* iif;
+  const int64_t* label;
+  const float* cw;
+  const float* sw;
+  int64_t ignore_index;
+  float scale;
+  int64_t B; int C;
+  float* loss_i; float* loss_sum;
+  float* dz32; int64_t lddz32;
+  uint16_t* dz16; int64_t lddz16;
+  float* lse; int32_t* argmax; int32_t* rank; int32_t* acc_counts; int32_t* scratch;
+  float* out; int64_t ldo; int softmax; int on_scaled;
+};
+
+// Fill the arguments of the softmax-CE rows; returns whether the 128-bit (VEC) path is legal.
+inline bool make_ce_row_args(RowArgs& a, const float* z, int64_t ldz, const float* iifv, const int64_t* label,
+                             const float* class_weight, const float* sample_weight, int64_t ignore_index, float scale,
+                             int64_t B, int64_t C, float* loss_i, float* loss_sum, float* dz_f32, int64_t lddz_f32,
+                             void* dz_bf16, int64_t lddz_bf16, float* lse, int32_t* argmax, int32_t* rank,
+                             int32_t* acc_counts, int32_t* scratch) {
+  a = RowArgs{};
+  a.z = z; a.ldz = ldz; a.iif = iifv; a.label = label; a.cw = class_weight; a.sw = sample_weight;
+  a.ignore_index = ignore_index; a.scale = scale; a.B = B; a.C = (int)C;
+  a.loss_i = loss_i; a.loss_sum = loss_sum; a.dz32 = dz_f32; a.lddz32 = lddz_f32;
+  a.dz16 = reinterpret_cast<uint16_t*>(dz_bf16); a.lddz16 = lddz_bf16; a.lse = lse; a.argmax = argmax; a.rank = rank;
+  a.acc_counts = acc_counts; a.scratch = scratch; a.on_scaled = 0;
+  return (C % 4 == 0) && (ldz % 4 == 0) && aligned16(z) && (!iifv || aligned16(iifv)) &&
+         (!dz_f32 || (aligned16(dz_f32) && lddz_f32 % 4 == 0)) &&
+         (!dz_bf16 || ((reinterpret_cast<uintptr_t>(dz_bf16) & 7u) == 0 && lddz_bf16 % 4 == 0));
+}
+
+// scratch layout: [0] ticket (zero on entry, reset on exit) | 16: double part[grid] | int c1[grid] | int c5[grid]
+__host__ __device__ inline size_t scratch_bytes_for(int64_t grid) { return 16 + (size_t)grid * 16; }
+
+template <int THREADS>
+__device__ __forceinline__ double block_sum_d(double v, double* s) {   // fixed order: deterministic
+  v = warp_sum_d(v);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) r += s[w];
+  __syncthreads();
+  return r;
+}
+template <int THREADS>
+__device__ __forceinline__ int block_sum_i(int v, int* s) {
+  v = warp_sum_i(v);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) r += s[w];
+  __syncthreads();
+  return r;
+}
+
+// Grid-wide tail: every CTA has published one partial (loss sum, top-1 / top-5 hits); the last CTA
+// to take a ticket adds them in index order.  Only thread 0 fences -- the dZ stores of the other
+// threads are ordered by the kernel boundary, not by this reduction.
+// Returns true (CTA-uniform) in the last CTA, after the totals are written.
+template <int THREADS>
+__device__ __forceinline__ bool grid_tail(double part, int c1, int c5, float* loss_sum, int32_t* acc_counts,
+                                          int32_t* scratch) {
+  __shared__ int s_last;
+  __shared__ double s_d[THREADS / 32];
+  __shared__ int s_i[THREADS / 32];
+  double* g_part = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(scratch) + 16);
+  int* g_c1 = reinterpret_cast<int*>(g_part + gridDim.x);
+  int* g_c5 = g_c1 + gridDim.x;
+  if (threadIdx.x == 0) {
+    __stcg(g_part + blockIdx.x, part);
+    __stcg(g_c1 + blockIdx.x, c1);
+    __stcg(g_c5 + blockIdx.x, c5);
+    __threadfence();
+    s_last = (atomicAdd(scratch, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double acc = 0.0;
+  int k1 = 0, k5 = 0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) {
+    acc += __ldcg(g_part + i); k1 += __ldcg(g_c1 + i); k5 += __ldcg(g_c5 + i);
+  }
+  acc = block_sum_d<THREADS>(acc, s_d);
+  k1 = block_sum_i<THREADS>(k1, s_i);
+  k5 = block_sum_i<THREADS>(k5, s_i);
+  if (threadIdx.x == 0) {
+    if (loss_sum) *loss_sum = (float)acc;
+    if (acc_counts) { acc_counts[0] = k1; acc_counts[1] = k5; }
+    *scratch = 0;   // self-resetting ticket
+  }
+  return true;
+}
+
+// MODE 0: softmax-CE forward + backward.  MODE 1: activation (softmax(z*iif) or z*iif).
+// TPR threads share one row (NE elements each); a CTA of max(TPR,256) threads holds 256/TPR rows.
+// Small batches use wide rows (TPR = C/4: one 128-bit load per thread, short dependency chains, every
+// SM busy); large batches use NE = 8 for more bytes in flight per SM.
+template <int THREADS>
+struct RowSmem {
+  float f[3][THREADS / 32];
+  int i[THREADS / 32];
+};
+
+// The rows `row_block * (THREADS/TPR) ..` of one CTA.  Results for the row of this thread's group come
+// back in (my_loss, cnt, active); only the t == 0 thread of a row group needs them.
+template <int TPR, int NE, bool VEC, int MODE>
+__device__ __forceinline__ void softmax_row_body(const RowArgs& a, int64_t row_block,
+                                                 RowSmem<(TPR > 256 ? TPR : 256)>& sm, float& my_loss_out, int& cnt_out,
+                                                 bool& active_out) {
+  constexpr int THREADS = TPR > 256 ? TPR : 256;
+  constexpr int WPR = TPR / 32;            // warps per row
+  auto& s_f = sm.f;
+  auto& s_i = sm.i;
+  const int t = threadIdx.x % TPR;
+  const int lrow = threadIdx.x / TPR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w0 = (warp / WPR) * WPR;      // first warp of this row
+  const int64_t row = row_block * (THREADS / TPR) + lrow;
+  const bool active = row < a.B;
+  const int C = a.C;
+  const float* zr = a.z + (active ? row : 0) * a.ldz;
+  const bool want_rank = a.rank != nullptr, want_arg = a.argmax != nullptr;
+
+  int64_t y = -1;
+  if (active && a.label) y = __ldg(a.label + row);
+  const bool y_in = active && y >= 0 && y < C;
+  const bool y_ok = y_in && y != a.ignore_index;
+  const int yi = y_in ? (int)y : -1;
+  // label-dependent scalars: issued now, consumed after the reductions
+  const float sy = (y_in && a.iif) ? __ldg(a.iif + y) : 1.f;
+  float g = 0.f;
+  if (MODE == 0 && y_ok) {
+    g = a.scale;
+    if (a.cw) g *= __ldg(a.cw + y);
+    if (a.sw) g *= __ldg(a.sw + row);
+  }
+
+  float v[NE];                             // raw logits, later exp(scaled - max)
+  if constexpr (VEC) {
+#pragma unroll
+    for (int q = 0; q < NE / 4; ++q) {
+      const int col = (q * TPR + t) * 4;
+      float4 z4 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+      if (active && col < C) z4 = ldg_stream4(zr + col);
+      v[4 * q] = z4.x; v[4 * q + 1] = z4.y; v[4 * q + 2] = z4.z; v[4 * q + 3] = z4.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int col = e * TPR + t;
+      v[e] = (active && col < C) ? __ldg(zr + col) : -CUDART_INF_F;
+    }
+  }
+  auto col_of = [&](int e) { return VEC ? ((e >> 2) * TPR + t) * 4 + (e & 3) : e * TPR + t; };
+  auto scale_of = [&](int e) -> float {
+    const int col = col_of(e);
+    return (a.iif && col < C) ? __ldg(a.iif + col) : 1.f;
+  };
+
+  // ---- pass 1: row max of the scaled logits, arg max, the label's raw logit
+  float m = -CUDART_INF_F, bv = -CUDART_INF_F, zy = -CUDART_INF_F;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int col = col_of(e);
+    const bool in = active && col < C;
+    const float z = v[e];
+    const float sc = in ? z * scale_of(e) : -CUDART_INF_F;
+    m = fmaxf(m, sc);
+    if (want_arg) {
+      const float cmp = a.on_scaled ? sc : z;
+      if (in && cmp > bv) { bv = cmp; bi = col; }
+    }
+    if (in && col == yi) zy = z;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    zy = fmaxf(zy, __shfl_xor_sync(0xffffffffu, zy, o));
+    if (want_arg) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+  }
+  if constexpr (WPR > 1) {
+    if (lane == 0) { s_f[0][warp] = m; s_f[1][warp] = zy; s_f[2][warp] = bv; s_i[warp] = bi; }
+    __syncthreads();
+    m = s_f[0][w0]; zy = s_f[1][w0]; bv = s_f[2][w0]; bi = s_i[w0];
+#pragma unroll
+    for (int w = 1; w < WPR; ++w) {
+      m = fmaxf(m, s_f[0][w0 + w]);
+      zy = fmaxf(zy, s_f[1][w0 + w]);
+      const float ov = s_f[2][w0 + w]; const int oi = s_i[w0 + w];
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+  }
+  if (yi < 0) zy = 0.f;
+
+  if (MODE == 1 && !a.softmax) {
+    // out = z * iif  (cls/custom.py:38)
+    float* o = a.out + (active ? row : 0) * a.ldo;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) v[e] *= scale_of(e);
+    if constexpr (VEC) {
+#pragma unroll
+      for (int q = 0; q < NE / 4; ++q) {
+        const int col = (q * TPR + t) * 4;
+        if (active && col < C) stg_stream4(o + col, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int col = e * TPR + t;
+        if (active && col < C) o[col] = v[e];
+      }
+    }
+  }
+
+  // ---- pass 2: exp-sum; rank of the label (needs the label's logit, now known)
+  const float mm = (m == -CUDART_INF_F) ? 0.f : m;
+  const float ref = a.on_scaled ? zy * sy : zy;
+  float sum = 0.f;
+  int cnt = 0;
+  const bool need_exp = !(MODE == 1 && !a.softmax);
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const int col = col_of(e);
+    const bool in = active && col < C;
+    const float z = (MODE == 1 && !a.softmax) ? v[e] : v[e];   // activation mode already holds z*iif
+    const float sc = (MODE == 1 && !a.softmax) ? z : (in ? z * scale_of(e) : -CUDART_INF_F);
+    if (want_rank) {
+      const float cmp = (a.on_scaled || (MODE == 1 && !a.softmax)) ? sc : z;
+      cnt += in && ((cmp > ref) || (cmp == ref && col < yi));
+    }
+    if (need_exp) {
+      const float ex = in ? expf(sc - mm) : 0.f;
+      v[e] = ex;
+      sum += ex;
+    }
+  }
+  sum = warp_sum(sum);
+  if (want_rank) cnt = warp_sum_i(cnt);
+  if constexpr (WPR > 1) {
+    if (lane == 0) { s_f[0][warp] = sum; s_i[warp] = cnt; }
+    __syncthreads();
+    sum = s_f[0][w0]; cnt = s_i[w0];
+#pragma unroll
+    for (int w = 1; w < WPR; ++w) { sum += s_f[0][w0 + w]; cnt += s_i[w0 + w]; }
+  }
+  if (yi < 0) cnt = C;  // label outside [0,C): never inside any top-k
+
+  float my_loss = 0.f;
+  if (need_exp) {
+    const float inv = 1.f / sum;
+    if constexpr (MODE == 1) {
+      float* o = a.out + (active ? row : 0) * a.ldo;
+      if constexpr (VEC) {
+#pragma unroll
+        for (int q = 0; q < NE / 4; ++q) {
+          const int col = (q * TPR + t) * 4;
+          if (active && col < C)
+            stg_stream4(o + col, make_float4(v[4 * q] * inv, v[4 * q + 1] * inv, v[4 * q + 2] * inv, v[4 * q + 3] * inv));
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          const int col = e * TPR + t;
+          if (active && col < C) o[col] = v[e] * inv;
+        }
+      }
+    } else {
+      const float lse = mm + logf(sum);
+      my_loss = y_ok ? g * (lse - zy * sy) : 0.f;
+      if (active && t == 0) {
+        if (a.loss_i) a.loss_i[row] = my_loss;
+        if (a.lse) a.lse[row] = lse;
+      }
+      if (a.dz32 || a.dz16) {
+        float* d32 = a.dz32 ? a.dz32 + (active ? row : 0) * a.lddz32 : nullptr;
+        uint16_t* d16 = a.dz16 ? a.dz16 + (active ? row : 0) * a.lddz16 : nullptr;
+        if constexpr (VEC) {
+#pragma unroll
+          for (int q = 0; q < NE / 4; ++q) {
+            const int col = (q * TPR + t) * 4;
+            if (active && col < C) {
+              float4 d;
+              d.x = scale_of(4 * q + 0) * g * (v[4 * q + 0] * inv - (col + 0 == yi ? 1.f : 0.f));
+              d.y = scale_of(4 * q + 1) * g * (v[4 * q + 1] * inv - (col + 1 == yi ? 1.f : 0.f));
+              d.z = scale_of(4 * q + 2) * g * (v[4 * q + 2] * inv - (col + 2 == yi ? 1.f : 0.f));
+              d.w = scale_of(4 * q + 3) * g * (v[4 * q + 3] * inv - (col + 3 == yi ? 1.f : 0.f));
+              if (!y_ok) d = make_float4(0.f, 0.f, 0.f, 0.f);  // ignored row: exact zeros even for inf weights
+              if (d32) stg_stream4(d32 + col, d);
+              if (d16) stg_stream2(d16 + col, pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const int col = e * TPR + t;
+            if (active && col < C) {
+              float d = scale_of(e) * g * (v[e] * inv - (col == yi ? 1.f : 0.f));
+              if (!y_ok) d = 0.f;
+              if (d32) d32[col] = d;
+              if (d16) d16[col] = bf16_bits(d);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (active && t == 0) {
+    if (want_arg) a.argmax[row] = bi;
+    if (want_rank) a.rank[row] = cnt;
+  }
+  my_loss_out = my_loss;
+  cnt_out = cnt;
+  active_out = active;
+}
+
+}  // namespace iif

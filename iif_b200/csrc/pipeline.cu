@@ -1,0 +1,121 @@
+// Host-batch pipeline of the head step: the call a training loop makes when the step's features and
+// labels sit in (pinned) HOST memory.  Three library-owned streams overlap, slot by slot,
+//   h2d     : features + labels  host -> device          (copy engine, PCIe)
+//   compute : fc_cls -> IIF softmax-CE fwd+bwd -> dX, dW, db   (the 3 launches of iif_head_fwd_bwd_bf16)
+//   d2h     : the step's loss    device -> host           (copy engine)
+// so step i+1's 1 MB feature copy hides under step i's kernels.  All GEMM launches stay on ONE compute
+// stream: the split-K rendezvous of gemm_tc.cu needs a grid to itself (two such grids running
+// concurrently could starve each other of resident-CTA slots), and one workspace serves every slot.
+#include <new>
+
+#include "common.cuh"
+
+struct iif_pipeline {
+  struct Slot {
+    iif_head_args a;
+    cudaEvent_t h2d_done, step_done, loss_done, release;
+    bool used, held;
+  };
+  int nslots;
+  cudaStream_t s_h2d, s_compute, s_d2h;
+  Slot* slots;
+};
+
+#define IIF_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+extern "C" int iif_pipeline_create(iif_pipeline** out, const iif_head_args* slot_args, int nslots) {
+  if (!out || !slot_args || nslots < 1 || nslots > 64) return IIF_EINVAL;
+  for (int i = 0; i < nslots; ++i) {
+    const iif_head_args& a = slot_args[i];
+    if (!a.x || !a.w || !a.label || !a.z || !a.dz_bf16 || !a.dw || !a.loss_sum || a.B <= 0 || a.D <= 0 || a.C <= 0 ||
+        a.ldx < a.D)
+      return IIF_EINVAL;
+  }
+  iif_pipeline* p = new (std::nothrow) iif_pipeline();
+  if (!p) return IIF_EINVAL;
+  p->nslots = nslots;
+  p->slots = new (std::nothrow) iif_pipeline::Slot[nslots]();
+  if (!p->slots) { delete p; return IIF_EINVAL; }
+  IIF_CU(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+  IIF_CU(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
+  IIF_CU(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < nslots; ++i) {
+    iif_pipeline::Slot& s = p->slots[i];
+    s.a = slot_args[i];
+    IIF_CU(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+    IIF_CU(cudaEventCreateWithFlags(&s.step_done, cudaEventDisableTiming));
+    IIF_CU(cudaEventCreateWithFlags(&s.loss_done, cudaEventDisableTiming));
+    IIF_CU(cudaEventCreateWithFlags(&s.release, cudaEventDisableTiming));
+  }
+  *out = p;
+  return IIF_OK;
+}
+
+extern "C" int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x, const int64_t* host_label,
+                                   float* host_loss) {
+  if (!p || slot < 0 || slot >= p->nslots || !host_x || !host_label || !host_loss) return IIF_EINVAL;
+  iif_pipeline::Slot& s = p->slots[slot];
+  const iif_head_args& a = s.a;
+  // the slot's device buffers are free once its previous step (and whoever held its gradients) is done
+  if (s.used) IIF_CU(cudaStreamWaitEvent(p->s_h2d, s.loss_done, 0));
+  if (s.held) { IIF_CU(cudaStreamWaitEvent(p->s_h2d, s.release, 0)); s.held = false; }
+  if (a.ldx == a.D)
+    IIF_CU(cudaMemcpyAsync(const_cast<void*>(a.x), host_x, (size_t)a.B * a.D * 2, cudaMemcpyHostToDevice, p->s_h2d));
+  else
+    IIF_CU(cudaMemcpy2DAsync(const_cast<void*>(a.x), (size_t)a.ldx * 2, host_x, (size_t)a.D * 2, (size_t)a.D * 2, a.B,
+                             cudaMemcpyHostToDevice, p->s_h2d));
+  IIF_CU(cudaMemcpyAsync(const_cast<int64_t*>(a.label), host_label, (size_t)a.B * 8, cudaMemcpyHostToDevice, p->s_h2d));
+  IIF_CU(cudaEventRecord(s.h2d_done, p->s_h2d));
+  IIF_CU(cudaStreamWaitEvent(p->s_compute, s.h2d_done, 0));
+  if (int rc = iif_head_fwd_bwd_bf16(&a, p->s_compute)) return rc;
+  IIF_CU(cudaEventRecord(s.step_done, p->s_compute));
+  IIF_CU(cudaStreamWaitEvent(p->s_d2h, s.step_done, 0));
+  IIF_CU(cudaMemcpyAsync(host_loss, a.loss_sum, 4, cudaMemcpyDeviceToHost, p->s_d2h));
+  IIF_CU(cudaEventRecord(s.loss_done, p->s_d2h));
+  s.used = true;
+  return IIF_OK;
+}
+
+extern "C" int iif_pipeline_wait(iif_pipeline* p, int slot) {
+  if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  if (!p->slots[slot].used) return IIF_OK;
+  IIF_CU(cudaEventSynchronize(p->slots[slot].loss_done));
+  return IIF_OK;
+}
+
+extern "C" int iif_pipeline_stream_wait_step(iif_pipeline* p, int slot, void* stream) {
+  if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  if (p->slots[slot].used) IIF_CU(cudaStreamWaitEvent((cudaStream_t)stream, p->slots[slot].step_done, 0));
+  return IIF_OK;
+}
+
+extern "C" int iif_pipeline_hold_slot(iif_pipeline* p, int slot, void* stream) {
+  if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  IIF_CU(cudaEventRecord(p->slots[slot].release, (cudaStream_t)stream));
+  p->slots[slot].held = true;
+  return IIF_OK;
+}
+
+extern "C" int iif_pipeline_sync(iif_pipeline* p) {
+  if (!p) return IIF_EINVAL;
+  IIF_CU(cudaStreamSynchronize(p->s_h2d));
+  IIF_CU(cudaStreamSynchronize(p->s_compute));
+  IIF_CU(cudaStreamSynchronize(p->s_d2h));
+  return IIF_OK;
+}
+
+extern "C" void iif_pipeline_destroy(iif_pipeline* p) {
+  if (!p) return;
+  iif_pipeline_sync(p);
+  for (int i = 0; i < p->nslots; ++i) {
+    cudaEventDestroy(p->slots[i].h2d_done);
+    cudaEventDestroy(p->slots[i].step_done);
+    cudaEventDestroy(p->slots[i].loss_done);
+    cudaEventDestroy(p->slots[i].release);
+  }
+  cudaStreamDestroy(p->s_h2d);
+  cudaStreamDestroy(p->s_compute);
+  cudaStreamDestroy(p->s_d2h);
+  delete[] p->slots;
+  delete p;
+}

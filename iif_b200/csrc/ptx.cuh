@@ -97,6 +97,16 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long atom_add_release_u64(unsigned long long* p, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.release.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 // Spin until *p >= target.  Only used between CTAs of ONE grid that are co-resident by construction
 // (the host caps the grid at the device's resident-CTA capacity); bounded like mbar_wait.
 __device__ __forceinline__ void spin_until_ge(const int* p, int target) {
@@ -105,6 +115,17 @@ __device__ __forceinline__ void spin_until_ge(const int* p, int target) {
   while (ld_acquire(p) < target) {
     if (clock64() - t0 > 4000000000ll) {
       printf("iif_b200: inter-CTA flag wait timed out (block %d thread %d): workspace header not zeroed?\n", blockIdx.x,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void spin_until_ge_u64(const unsigned long long* p, unsigned long long target) {
+  if (ld_acquire_u64(p) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_u64(p) < target) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("iif_b200: split-K rendezvous timed out (block %d thread %d): workspace header not zeroed?\n", blockIdx.x,
              threadIdx.x);
       __trap();
     }

@@ -363,7 +363,8 @@ class HeadStep:
     once so the step can be captured in a CUDA graph.  dW and db live in ONE flat fp32 buffer
     (`grad_flat`) so the data-parallel all-reduce of the head's parameter gradients is one message."""
 
-    def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False, ws=None):
+    def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False, ws=None,
+                 fused_loss=True, stable_operands=False):
         dev = torch.device(device)
         self.B, self.D, self.C, self.device = B, D, Cc, dev
         f32, i32 = torch.float32, torch.int32
@@ -385,7 +386,11 @@ class HeadStep:
         self.ws = ws if ws is not None else torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
         self.ws_bytes = n
         self.dx_dtype = _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32
-        self.launches_per_step = 3
+        self.fused_loss = bool(fused_loss)
+        # promise that x / w are not written by the launch preceding each step on the stream (see
+        # IIF_HEAD_STABLE_OPERANDS): lets the GEMMs prefetch them under the previous kernel's tail
+        self.stable_operands = bool(stable_operands)
+        self.launches_per_step = 3     # refined by bind(): 2 when the loss rows ride in the backward launch
         self._args = None
         self._keep = None
 
@@ -427,6 +432,12 @@ class HeadStep:
         a.acc_counts = None if self.acc_counts is None else self.acc_counts.data_ptr()
         a.scratch = self.scratch.data_ptr()
         a.ws, a.ws_bytes = self.ws.data_ptr(), self.ws_bytes
+        a.flags = (0 if self.fused_loss else _lib.HEAD_NO_FUSED_LOSS) | \
+                  (_lib.HEAD_STABLE_OPERANDS if self.stable_operands else 0)
+        n = int(_lib.load().iif_head_launches(C.byref(a)))
+        if n < 0:
+            _lib.check(n, "head_launches")
+        self.launches_per_step = n
         self._args = a
         self._keep = (x, w, bias, iif, label, class_weight, sample_weight)
         self._fn = _lib.load().iif_head_fwd_bwd_bf16
@@ -451,12 +462,79 @@ class HeadStep:
         p = C.c_void_p
         out = [("linear_fwd_bf16", lambda: lib.iif_linear_fwd_bf16(p(a.x), a.ldx, p(a.w), a.ldw, p(a.bias), None,
                                                                    p(a.z), a.ldz, None, 0, a.B, a.D, a.C, p(a.ws),
-                                                                   a.ws_bytes, st())),
-               ("softmax_ce_fwd_bwd", lambda: lib.iif_softmax_ce_fwd_bwd(
-                   p(a.z), a.ldz, p(a.iif), p(a.label), p(a.class_weight), p(a.sample_weight), a.ignore_index, a.scale,
-                   a.B, a.C, p(a.loss_i), p(a.loss_sum), None, 0, p(a.dz_bf16), a.lddz, None, p(a.argmax), p(a.rank),
-                   p(a.acc_counts), p(a.scratch), st()))]
+                                                                   a.ws_bytes, st()))]
+        if self.launches_per_step == 2:
+            out.append(("loss_linear_bwd_bf16", lambda: lib.iif_loss_linear_bwd_bf16(C.byref(a), st())))
+            return out
+        out.append(("softmax_ce_fwd_bwd", lambda: lib.iif_softmax_ce_fwd_bwd(
+            p(a.z), a.ldz, p(a.iif), p(a.label), p(a.class_weight), p(a.sample_weight), a.ignore_index, a.scale,
+            a.B, a.C, p(a.loss_i), p(a.loss_sum), None, 0, p(a.dz_bf16), a.lddz, None, p(a.argmax), p(a.rank),
+            p(a.acc_counts), p(a.scratch), st())))
         out.append(("linear_bwd_bf16", lambda: lib.iif_linear_bwd_bf16(
             p(a.dz_bf16), a.lddz, p(a.x), a.ldx, p(a.w), a.ldw, None, p(a.dx), a.dx_dtype, a.lddx, p(a.dw), a.lddw,
             p(a.db), a.B, a.D, a.C, p(a.ws), a.ws_bytes, st())))
         return out
+
+class HeadPipeline:
+    """Host-batch pipeline over bound `HeadStep` slots (C: iif_pipeline_*, csrc/pipeline.cu).
+
+    `submit(slot, host_x, host_label)` enqueues H2D copy -> head step -> D2H of the loss on three
+    library-owned streams and returns at once; `wait(slot)` blocks until that step's loss is in host
+    memory and returns it.  Consecutive slots overlap: the next batch's PCIe copy hides under the
+    current step's kernels.  This is the loop of cls/train.py:66-77 (batch from the loader ->
+    criterion -> loss.item()) for the head alone."""
+
+    def __init__(self, steps):
+        if not steps or any(hs._args is None for hs in steps):
+            raise ValueError("HeadPipeline needs bound HeadStep slots")
+        self.steps = list(steps)
+        n = len(self.steps)
+        arr = (_lib.HeadArgs * n)()
+        for i, hs in enumerate(self.steps):
+            arr[i] = hs._args
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        torch.cuda.synchronize(self.steps[0].device)      # the slots' buffers were produced on torch streams
+        _lib.check(self._lib.iif_pipeline_create(C.byref(self._h), arr, n), "pipeline_create")
+        self.host_loss = torch.zeros(n, dtype=torch.float32).pin_memory()
+        self._loss_ptr = self.host_loss.data_ptr()
+
+    def submit(self, slot: int, host_x: torch.Tensor, host_label: torch.Tensor) -> None:
+        hs = self.steps[slot]
+        if host_x.is_cuda or host_label.is_cuda:
+            raise RuntimeError("HeadPipeline.submit takes HOST tensors (use HeadStep.launch for device inputs)")
+        if host_x.dtype != torch.bfloat16 or tuple(host_x.shape) != (hs.B, hs.D) or not host_x.is_contiguous():
+            raise ValueError(f"host_x must be a contiguous bf16 [{hs.B},{hs.D}] tensor")
+        if host_label.dtype != torch.int64 or host_label.numel() != hs.B or not host_label.is_contiguous():
+            raise ValueError(f"host_label must be a contiguous int64 [{hs.B}] tensor")
+        rc = self._lib.iif_pipeline_submit(self._h, slot, host_x.data_ptr(), host_label.data_ptr(),
+                                           self._loss_ptr + 4 * slot)
+        if rc:
+            _lib.check(rc, "pipeline_submit")
+
+    def wait(self, slot: int) -> float:
+        rc = self._lib.iif_pipeline_wait(self._h, slot)
+        if rc:
+            _lib.check(rc, "pipeline_wait")
+        return float(self.host_loss[slot])
+
+    def stream_wait_step(self, slot: int, stream: torch.cuda.Stream) -> None:
+        _lib.check(self._lib.iif_pipeline_stream_wait_step(self._h, slot, C.c_void_p(stream.cuda_stream)),
+                   "pipeline_stream_wait_step")
+
+    def hold_slot(self, slot: int, stream: torch.cuda.Stream) -> None:
+        _lib.check(self._lib.iif_pipeline_hold_slot(self._h, slot, C.c_void_p(stream.cuda_stream)), "pipeline_hold_slot")
+
+    def sync(self) -> None:
+        _lib.check(self._lib.iif_pipeline_sync(self._h), "pipeline_sync")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.iif_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -204,9 +204,12 @@ IIF_API int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int
                         const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw, int64_t lddw,
                         float* db, int64_t B, int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream);
 
-/* Debug hook: when `buf` (device, 16 int64 per CTA of the next tensor-core launches) is non-NULL every CTA
- * records %globaltimer at its phase boundaries (tools/tc_timing.py); NULL switches it off. */
+/* Debug hooks (tools/tc_timing.py).  iif_debug_timing: when `buf` (device, 16 int64 per CTA of the next
+ * tensor-core launches) is non-NULL every CTA records %globaltimer at its phase boundaries; NULL switches
+ * it off.  iif_debug_capacity: resident-CTA capacity of the current device for the tensor-core kernel
+ * (the split-K rendezvous is only enabled for grids that fit it). */
 IIF_API void iif_debug_timing(long long* buf);
+IIF_API int iif_debug_capacity(int* detail6 /* host, optional: occupancy API, by smem, by regs, regs, smem/SM, static smem */);
 
 /* Workspace (bytes) the three bf16 GEMMs of a head of this shape may need (max over the three). */
 IIF_API size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C);
@@ -238,12 +241,52 @@ typedef struct iif_head_args {
   /* scratch */
   int32_t* scratch;                   /* iif_loss_scratch_bytes(B), first int32 zero */
   void* ws; size_t ws_bytes;          /* iif_gemm_ws_bytes(B,D,C) */
+  int32_t flags;                      /* IIF_HEAD_* */
 } iif_head_args;
 
 /* Launches the 3 kernels of one head step on `stream` (fc_cls GEMM; fused loss; dX+dW+db GEMM group),
  * chained by programmatic dependent launch (cls/train.py:66-77 collapsed to the head;
  * seg/.../bbox_head.py:118 + :269-274 + autograd). */
+#define IIF_HEAD_NO_FUSED_LOSS 1      /* keep the loss rows in their own launch (3 launches per step) */
+/* Caller's promise: x and w are NOT written by the kernel launch that immediately precedes this call on
+ * `stream` (true for a training loop whose previous launch on the stream is this library's own backward,
+ * or whose inputs arrive by copies / events).  The GEMM kernels then request their x / w tiles before the
+ * programmatic-dependency wait, hiding the HBM latency under the predecessor's tail. */
+#define IIF_HEAD_STABLE_OPERANDS 2
 IIF_API int iif_head_fwd_bwd_bf16(const iif_head_args* args, void* stream);
+/* The loss rows + AddmmBackward in ONE launch: every CTA of the backward launch first computes its share
+ * of the softmax-CE rows (reads args->z, writes loss_i / dz_bf16 / argmax / rank), the grid meets at a
+ * counter in the workspace header, then dX, dW, db are formed from dZ out of L2.  The X / W operand tiles
+ * are requested before the loss rows run.  Returns IIF_EUNSUPPORTED (nothing launched) when the shape
+ * does not qualify: grid above the resident-CTA capacity, C > 4096 or C % 4 != 0, unaligned rows. */
+IIF_API int iif_loss_linear_bwd_bf16(const iif_head_args* args, void* stream);
+/* Number of launches iif_head_fwd_bwd_bf16 makes for these arguments (2 or 3); negative = argument error. */
+IIF_API int iif_head_launches(const iif_head_args* args);
+
+/* ---------------------------------------------------------------------------------------------
+ * host-batch pipeline: the head step with the step's features / labels in (pinned) HOST memory.
+ * `slot_args[i]` describes slot i's DEVICE buffers exactly as for iif_head_fwd_bwd_bf16 (x and label
+ * are the device staging buffers the host batch is copied into; w, bias, iif are shared parameters;
+ * ws may be shared by all slots).  Per submit: H2D of x [B,D] bf16 and label [B] int64 on a copy
+ * stream, the three launches of the step on the library's single compute stream, D2H of the loss
+ * scalar on a third stream -- slot i+1's copy overlaps slot i's kernels.  This is the data-loader ->
+ * criterion(output, target) -> loss.item() sequence of cls/train.py:66-77 for the head alone.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct iif_pipeline iif_pipeline;
+IIF_API int iif_pipeline_create(iif_pipeline** out, const iif_head_args* slot_args, int nslots);
+/* Enqueue one step on `slot` (waits, on the device, for the slot's previous step). host_x: [B,D] bf16
+ * contiguous, host_label: [B] int64, host_loss: 4 bytes; all three should be pinned. Never blocks. */
+IIF_API int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x, const int64_t* host_label,
+                                float* host_loss);
+/* Block until the slot's latest step has delivered its loss to host_loss. */
+IIF_API int iif_pipeline_wait(iif_pipeline* p, int slot);
+/* Make `stream` wait for the slot's latest step (its gradients are then complete) ... */
+IIF_API int iif_pipeline_stream_wait_step(iif_pipeline* p, int slot, void* stream);
+/* ... and keep the slot's buffers untouched until the work queued so far on `stream` (the
+ * all-reduce of its gradients) has finished. */
+IIF_API int iif_pipeline_hold_slot(iif_pipeline* p, int slot, void* stream);
+IIF_API int iif_pipeline_sync(iif_pipeline* p);
+IIF_API void iif_pipeline_destroy(iif_pipeline* p);
 
 #ifdef __cplusplus
 }

@@ -297,3 +297,55 @@ def test_fused_head_bf16(B, D, C, relu):
     assert rel_err(N(hs.db), ref16["db"]) < 6e-3
     assert np.array_equal(hs.argmax.cpu().numpy(), ho.argmax_first(N(hs.z)))      # bit-exact on its own logits
     assert np.array_equal(hs.rank.cpu().numpy(), ho.label_rank(N(hs.z), y))
+
+
+@pytest.mark.parametrize("B,D,C", [(256, 2048, 1000), (1024, 1024, 1204), (77, 520, 1204), (512, 512, 4096), (300, 256, 8)])
+def test_loss_fused_into_backward_launch(B, D, C):
+    """The loss rows riding in the backward launch (iif_loss_linear_bwd_bf16: 2 launches per step) give
+    bit-identical dZ / loss_i / argmax / rank and the same loss, dX, dW, db as the 3-launch chain; the
+    workspace counters re-arm themselves (several steps back to back on one workspace)."""
+    from iif_b200.ops import HeadStep
+    x, w, b, counts, y = head_inputs(B, D, C, seed=B + C)
+    iif = iif_row(counts, "raw")
+    y[::7] = -100                                     # ignored rows
+    bf = torch.bfloat16
+    args = (T(x, bf), T(w, bf), T(b), T(iif).reshape(-1), T(y))
+    a = HeadStep(B, D, C, DEV, want_acc=True, fused_loss=True)
+    u = HeadStep(B, D, C, DEV, want_acc=True, fused_loss=False)
+    a.bind(*args); u.bind(*args)
+    assert u.launches_per_step == 3
+    assert a.launches_per_step == 2, "this shape is expected to qualify for the fused launch"
+    for _ in range(3):
+        la, lu = a.launch(), u.launch()
+    torch.cuda.synchronize()
+    assert torch.equal(a.z, u.z) and torch.equal(a.dz[:, :C], u.dz[:, :C]) and torch.equal(a.loss_i, u.loss_i)
+    assert torch.equal(a.argmax, u.argmax) and torch.equal(a.rank, u.rank) and torch.equal(a.acc_counts, u.acc_counts)
+    assert float(la) == pytest.approx(float(lu), rel=1e-6)
+    assert torch.equal(a.dw, u.dw) and torch.equal(a.db, u.db)
+    assert rel_err(N(a.dx), N(u.dx)) < 1e-6           # the K split of dX may differ between the two grids
+
+
+def test_head_step_stable_operands_prefetch():
+    """IIF_HEAD_STABLE_OPERANDS: x / w tiles requested before the programmatic-dependency wait.  Steps run
+    back to back (the predecessor of every forward is this library's own backward launch) and must
+    reproduce the conservative path bit for bit."""
+    from iif_b200.ops import HeadStep
+    B, D, C = 256, 2048, 1000
+    bf = torch.bfloat16
+    ref = HeadStep(B, D, C, DEV, want_acc=True)
+    pre = HeadStep(B, D, C, DEV, want_acc=True, stable_operands=True)
+    outs = []
+    for seed in range(3):
+        x, w, b, counts, y = head_inputs(B, D, C, seed=seed)
+        iif = iif_row(counts, "smooth")
+        args = (T(x, bf), T(w, bf), T(b), T(iif).reshape(-1), T(y))
+        ref.bind(*args); pre.bind(*args)
+        torch.cuda.synchronize()
+        for _ in range(4):
+            lr = ref.launch()
+        for _ in range(4):
+            lp = pre.launch()
+        torch.cuda.synchronize()
+        assert float(lr) == float(lp)
+        assert torch.equal(ref.z, pre.z) and torch.equal(ref.dw, pre.dw) and torch.equal(ref.dx, pre.dx)
+        assert torch.equal(ref.db, pre.db) and torch.equal(ref.rank, pre.rank)

@@ -7,9 +7,13 @@ from iif_b200 import ops, _lib
 dev = "cuda:0"
 B, D, C = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256,2048,1000").split(","))
 lib = _lib.load()
+import ctypes
+_d = (ctypes.c_int * 6)()
+torch.zeros(1, device=dev)
+print("resident CTA capacity", lib.iif_debug_capacity(_d), "detail [api/SM, by smem, by regs, regs, smem/SM, static smem]", list(_d))
 bf = torch.bfloat16
 NAMES = ["start", "prologue", "griddep", "tma_issued", "first_full", "last_full", "acc_done", "partial_out",
-         "rendezvous", "end"]
+         "rendezvous", "end", "loss_rows_done", "grid_barrier"]
 
 def show(tag, fn, n_cta_max=4096):
     buf = torch.zeros(n_cta_max * 16, dtype=torch.int64, device=dev)
@@ -25,7 +29,7 @@ def show(tag, fn, n_cta_max=4096):
     t = buf.cpu().numpy().reshape(-1, 16)
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
-    print(f"== {tag}: {len(t)} CTAs, kernel span {(t[:, :10].max() - t0) / 1e3:.2f} us")
+    print(f"== {tag}: {len(t)} CTAs, kernel span {(t[:, :12].max() - t0) / 1e3:.2f} us")
     for i, n in enumerate(NAMES):
         col = t[:, i]
         col = col[col > 0]
@@ -38,6 +42,16 @@ dz = (torch.randn(B, ops.pad8(C), device=dev) / B).to(bf)[:, :C]
 show("fwd", lambda: ops.linear_fwd(x, w, bias))
 show("bwd group", lambda: ops.linear_bwd(dz, x, w, dx_bf16=True))
 show("dw only", lambda: ops.linear_bwd(dz, x, w, need_dx=False))
+y = torch.randint(0, C, (B,), device=dev)
+iif = torch.rand(C, device=dev) * 6 + 0.5
+for stable in (False, True):
+    hs = ops.HeadStep(B, D, C, dev, stable_operands=stable)
+    hs.bind(x, w, bias, iif, y)
+    k = dict(hs.kernels())
+    hs.launch(); torch.cuda.synchronize()
+    if "loss_linear_bwd_bf16" in k:
+        show(f"loss+bwd fused (stable_operands={stable})", k["loss_linear_bwd_bf16"])
+    show(f"fwd via head (stable_operands={stable})", k["linear_fwd_bf16"])
 for i in range(3):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(); ops.linear_fwd(x, w, bias); t1.record(); torch.cuda.synchronize()
