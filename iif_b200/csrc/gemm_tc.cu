@@ -99,7 +99,7 @@ struct TcGroup {
   TcProblem p[2];
   // loss-fused backward launch: every CTA first runs rows of the IIF softmax-CE (loss_row.cuh) that
   // PRODUCES the A operand (dZ), the grid meets at `grid_bar`, then the GEMMs consume dZ from L2.
-  int fuse_loss, loss_ne;
+  int fuse_loss, loss_ne, loss_prefetch;
   int* grid_bar;                         // arrival count, zero between launches
   RowArgs loss;
 };
@@ -168,6 +168,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) stamp(g, 0);
+  if (g.fuse_loss && g.loss_prefetch && (int64_t)blockIdx.x < g.loss.B) {
+    // inputs of the loss rows that no kernel writes (labels, IIF vector): pull them towards the SM now, the
+    // dependent label -> iif[label] hop then costs an L1 / L2 hit instead of two HBM round trips
+    if (threadIdx.x == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.loss.label + blockIdx.x));
+    if (g.loss.iif && (int)threadIdx.x * 32 < g.loss.C)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(g.loss.iif + threadIdx.x * 32));
+  }
   const int pi = (g.nprob > 1 && (int)blockIdx.x >= g.cta_begin[1]) ? 1 : 0;
   const TcProblem& P = g.p[pi];
   const CUtensorMap* tmA = pi ? &tmA1 : &tmA0;
@@ -264,10 +271,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncthreads();
     if (threadIdx.x == 0) {
       stamp(g, 10);
-      __threadfence();
+      // release (cumulative over the CTA's stores ordered by the barrier above) / acquire at gpu scope:
+      // no full __threadfence (MEMBAR.SC + L1 invalidate) on this path
       ptx::red_release_add(g.grid_bar, 1);
       ptx::spin_until_ge(g.grid_bar, (int)gridDim.x);   // every row of dZ is in L2
-      __threadfence();
       asm volatile("fence.proxy.async;" ::: "memory");
       stamp(g, 11);
     }
@@ -441,12 +448,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncthreads();                         // every thread's partial stores are issued ...
     if (threadIdx.x == 0) {
       stamp(g, 7);
-      __threadfence();                       // ... and made visible at gpu scope (cumulative) before the arrival
+      // ... and published by a gpu-scope RELEASE (cumulative over the CTA's stores ordered by the barrier);
+      // the matching ACQUIRE is the poll.  No __threadfence (MEMBAR.SC + L1 invalidate) on this path.
       const unsigned long long inc = EPOCH_UNIT / (unsigned)P.splits;
-      const unsigned long long old = ptx::atom_add_release_u64(arrive, inc);
+      const unsigned long long old = ptx::atom_add_acq_rel_u64(arrive, inc);
       const unsigned long long target = (old / EPOCH_UNIT + 1) * EPOCH_UNIT;
       if (old + inc < target) ptx::spin_until_ge_u64(arrive, target);
-      __threadfence();
       stamp(g, 8);
     }
     __syncthreads();
@@ -744,6 +751,7 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
     // the grid barrier needs every CTA resident; C <= 4096 with 256 threads per row
     if (cta > cap || loss->C > 4096 || (loss->C & 3) || !loss->scratch) return IIF_EUNSUPPORTED;
     g.fuse_loss = 1;
+    g.loss_prefetch = d[0].pre_b;            // the caller's "inputs are stable" promise
     g.loss_ne = loss->C <= 1024 ? 4 : (loss->C <= 2048 ? 8 : 16);
     g.grid_bar = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + 4096);
     g.loss = *loss;

@@ -85,12 +85,11 @@ __device__ __forceinline__ bool grid_tail(double part, int c1, int c5, float* lo
     __stcg(g_part + blockIdx.x, part);
     __stcg(g_c1 + blockIdx.x, c1);
     __stcg(g_c5 + blockIdx.x, c5);
-    __threadfence();
-    s_last = (atomicAdd(scratch, 1) == (int)gridDim.x - 1);
+    // release our partial / acquire everyone else's in one gpu-scope RMW (no MEMBAR.SC on the tail)
+    s_last = (ptx::atom_add_acq_rel(scratch, 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last) return false;
-  __threadfence();
   double acc = 0.0;
   int k1 = 0, k5 = 0;
   for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) {
