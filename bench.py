@@ -47,7 +47,6 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-loss", action="store_true", help="3 launches per step (loss rows in their own launch)")
-    ap.add_argument("--no-prefetch", action="store_true", help="do not request x / w tiles before the dependency wait")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--sync-allreduce", action="store_true", help="N>1: all-reduce on the compute stream (no overlap)")
     return ap.parse_args()
@@ -185,7 +184,7 @@ def main():
         y = torch.multinomial(prob, B, replacement=True, generator=g).to(dev)
         bias = torch.full((C,), 0.01, device=dev)
         hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws,
-                          fused_loss=not args.no_fused_loss, stable_operands=not args.no_prefetch)
+                          fused_loss=not args.no_fused_loss)
         hs.bind(x, w, bias, iif, y)
         sets.append(hs)
     launches_per_step = sets[0].launches_per_step

@@ -15,7 +15,6 @@ OK, EINVAL, EALIGN, EUNSUPPORTED, EWORKSPACE, EDRIVER = 0, -1, -2, -3, -4, -5
 VARIANT_IDS = {"raw": 0, "smooth": 1, "rel": 2, "prob": 2, "normit": 3, "gombit": 4, "base2": 5, "base10": 6}
 DTYPE_F32, DTYPE_BF16 = 0, 1
 HEAD_NO_FUSED_LOSS = 1
-HEAD_STABLE_OPERANDS = 2
 
 _p, _i64, _i32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t
 

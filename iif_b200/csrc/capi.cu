@@ -26,9 +26,8 @@ extern "C" const char* iif_error_string(int code) {
 extern "C" int iif_head_fwd_bwd_bf16(const iif_head_args* h, void* stream) {
   if (!h || !h->x || !h->w || !h->label || !h->z || !h->dz_bf16 || !h->dw) return IIF_EINVAL;
   if (h->lddz % 8 != 0) return IIF_EALIGN;
-  const bool stable = (h->flags & IIF_HEAD_STABLE_OPERANDS) != 0;
-  int rc = iif::linear_fwd_bf16_ex(h->x, h->ldx, h->w, h->ldw, h->bias, nullptr, h->z, h->ldz, nullptr, 0, h->B, h->D, h->C,
-                                   h->ws, h->ws_bytes, stream, stable);
+  int rc = iif_linear_fwd_bf16(h->x, h->ldx, h->w, h->ldw, h->bias, nullptr, h->z, h->ldz, nullptr, 0, h->B, h->D, h->C,
+                               h->ws, h->ws_bytes, stream);
   if (rc) return rc;
   if (!(h->flags & IIF_HEAD_NO_FUSED_LOSS)) {
     rc = iif_loss_linear_bwd_bf16(h, stream);
@@ -38,6 +37,6 @@ extern "C" int iif_head_fwd_bwd_bf16(const iif_head_args* h, void* stream) {
                               h->scale, h->B, h->C, h->loss_i, h->loss_sum, nullptr, 0, h->dz_bf16, h->lddz, nullptr,
                               h->argmax, h->rank, h->acc_counts, h->scratch, stream);
   if (rc) return rc;
-  return iif::linear_bwd_bf16_ex(h->dz_bf16, h->lddz, h->x, h->ldx, h->w, h->ldw, nullptr, h->dx, h->dx_dtype, h->lddx,
-                                 h->dw, h->lddw, h->db, h->B, h->D, h->C, h->ws, h->ws_bytes, stream, stable);
+  return iif_linear_bwd_bf16(h->dz_bf16, h->lddz, h->x, h->ldx, h->w, h->ldw, nullptr, h->dx, h->dx_dtype, h->lddx, h->dw,
+                             h->lddw, h->db, h->B, h->D, h->C, h->ws, h->ws_bytes, stream);
 }

@@ -17,14 +17,6 @@ inline int launch_status() {
   return e == cudaSuccess ? IIF_OK : (int)e;
 }
 
-// gemm_tc.cu: the public bf16 GEMM entry points plus the "operands are stable" promise of the head step
-int linear_fwd_bf16_ex(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* col_scale,
-                       float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B, int64_t D, int64_t C, void* ws,
-                       size_t ws_bytes, void* stream, bool stable);
-int linear_bwd_bf16_ex(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
-                       const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw, int64_t lddw, float* db,
-                       int64_t B, int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream, bool stable);
-
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kNumSMs = 148;  // B200

@@ -87,8 +87,6 @@ struct TcProblem {
   float* out2; int64_t ldo2;
   float4* partial;                                  // [tiles][splits][TILE_F4] fp32x4, layout part_idx()
   unsigned long long* counters;                     // [tiles] arrival epochs (see EPOCH_UNIT)
-  int pre_a, pre_b;                                 // operand not written by the preceding kernel: may be
-                                                    // requested before the programmatic-dependency wait
   float* db_out; float* db_partial;                 // dW only: db[m] (and [tiles_m][splits][TILE_M] partials)
 };
 
@@ -99,7 +97,7 @@ struct TcGroup {
   TcProblem p[2];
   // loss-fused backward launch: every CTA first runs rows of the IIF softmax-CE (loss_row.cuh) that
   // PRODUCES the A operand (dZ), the grid meets at `grid_bar`, then the GEMMs consume dZ from L2.
-  int fuse_loss, loss_ne, loss_prefetch;
+  int fuse_loss, loss_ne;
   int* grid_bar;                         // arrival count, zero between launches
   RowArgs loss;
 };
@@ -147,6 +145,10 @@ __device__ __forceinline__ void emit4(const TcProblem& P, int m, int n, float4 v
   }
 }
 
+// FUSE_NE: 0 = plain GEMM launch; 4 / 8 / 16 = loss-fused backward launch with that many logits per thread
+// of a 256-thread row (one instantiation each keeps the straight-line code small: these kernels live for
+// ~10 us, instruction-cache misses are visible in their profile).
+template <int FUSE_NE>
 __global__ void __launch_bounds__(256, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -168,13 +170,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) stamp(g, 0);
-  if (g.fuse_loss && g.loss_prefetch && (int64_t)blockIdx.x < g.loss.B) {
-    // inputs of the loss rows that no kernel writes (labels, IIF vector): pull them towards the SM now, the
-    // dependent label -> iif[label] hop then costs an L1 / L2 hit instead of two HBM round trips
-    if (threadIdx.x == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(g.loss.label + blockIdx.x));
-    if (g.loss.iif && (int)threadIdx.x * 32 < g.loss.C)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(g.loss.iif + threadIdx.x * 32));
-  }
   const int pi = (g.nprob > 1 && (int)blockIdx.x >= g.cta_begin[1]) ? 1 : 0;
   const TcProblem& P = g.p[pi];
   const CUtensorMap* tmA = pi ? &tmA1 : &tmA0;
@@ -239,31 +234,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::tma_load_2d(sa, tmA, full_bar(stage), k0, m0);
     }
   };
-  // Operands the preceding kernel of the stream does not write (caller's promise) are requested BEFORE the
-  // dependency wait: their HBM latency hides under the predecessor's tail.
-  const int early_a = (P.pre_a && !g.fuse_loss) ? n_first : 0;
-  const int early_b = (P.pre_b || g.fuse_loss) ? n_first : 0;
-  if (threadIdx.x == 0) {
-    if (P.pre_b) for (int i = 0; i < n_first; ++i) load_b(i, kb_begin + i);
-    for (int i = 0; i < early_a; ++i) load_a(i, kb_begin + i);
-  }
+  // (Requesting x / w tiles BEFORE the dependency wait was tried and removed: with a predecessor kernel
+  // still running, TMA loads issued ahead of griddepcontrol.wait were occasionally never delivered -- see
+  // DESIGN.md "what did not work".)
+  const int early_b = FUSE_NE ? n_first : 0;
   ptx::griddep_launch_dependents();      // the next kernel may start its own prologue now
   ptx::griddep_wait();                   // ... and ours ends here: the producer kernel's data is visible
   if (threadIdx.x == 0) stamp(g, 2);
 
   double loss_part = 0.0;
   int loss_c1 = 0, loss_c5 = 0;
-  if (g.fuse_loss) {
+  if constexpr (FUSE_NE != 0) {
     // ---- loss-fused launch: B operands (X / W tiles: independent of the loss) are requested first ...
-    if (threadIdx.x == 0 && !P.pre_b)
+    if (threadIdx.x == 0)
       for (int i = 0; i < n_first; ++i) load_b(i, kb_begin + i);
     // ---- ... then every CTA computes its share of the loss rows: Z -> loss_i, dZ (bf16, global)
     __shared__ RowSmem<256> row_sm;
     for (int64_t r = blockIdx.x; r < g.loss.B; r += gridDim.x) {
       float my_loss; int cnt; bool active;
-      if (g.loss_ne == 4) softmax_row_body<256, 4, true, 0>(g.loss, r, row_sm, my_loss, cnt, active);
-      else if (g.loss_ne == 8) softmax_row_body<256, 8, true, 0>(g.loss, r, row_sm, my_loss, cnt, active);
-      else softmax_row_body<256, 16, true, 0>(g.loss, r, row_sm, my_loss, cnt, active);
+      softmax_row_body<256, (FUSE_NE ? FUSE_NE : 4), true, 0>(g.loss, r, row_sm, my_loss, cnt, active);
       if (threadIdx.x == 0) { loss_part += (double)my_loss; loss_c1 += cnt < 1; loss_c5 += cnt < 5; }
       __syncthreads();
     }
@@ -287,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
         if (kb - kb_begin >= early_b) load_b(stage, kb);
-        if (kb - kb_begin >= early_a) load_a(stage, kb);
+        load_a(stage, kb);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       stamp(g, 3);                       // all TMA loads issued
@@ -497,7 +486,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
   if (threadIdx.x == 0) stamp(g, 9);
-  if (g.fuse_loss) {
+  if constexpr (FUSE_NE != 0) {
     // off the GEMMs' critical path: deterministic loss sum / top-k counts, then re-arm the grid barrier
     // (the ticket of the tail doubles as the "everyone is past the grid barrier" count: its last CTA re-arms it)
     if (grid_tail<256>(loss_part, loss_c1, loss_c5, g.loss.loss_sum, g.loss.acc_counts, g.loss.scratch) && threadIdx.x == 0)
@@ -571,6 +560,15 @@ static int make_map(CUtensorMap* out, const void* ptr, bool f32, uint64_t inner,
 
 // Resident-CTA capacity of the device for this kernel (2 per SM on B200): the split-K rendezvous
 // needs every CTA of the grid on an SM at the same time.
+static const void* kernel_variant(int v) {
+  switch (v) {
+    case 1: return reinterpret_cast<const void*>(&gemm_tc_kernel<4>);
+    case 2: return reinterpret_cast<const void*>(&gemm_tc_kernel<8>);
+    case 3: return reinterpret_cast<const void*>(&gemm_tc_kernel<16>);
+    default: return reinterpret_cast<const void*>(&gemm_tc_kernel<0>);
+  }
+}
+
 static int resident_capacity(int* detail = nullptr) {
   static std::mutex mu;
   static int caps[64] = {};              // per device ordinal; 0 = not yet queried
@@ -581,15 +579,23 @@ static int resident_capacity(int* detail = nullptr) {
   if (caps[dev] == 0) {
     int sms = 0, per_api = 0, smem_sm = 0, regs_sm = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
-      return 0;
-    // two ~100 KB CTAs per SM need the full shared-memory carve-out (the default sizes it for one)
-    cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_api, gemm_tc_kernel, 256, SMEM_BYTES);
+    int worst_regs = 0, worst_static = 0;
+    for (int v = 0; v < 4; ++v) {
+      const void* fn = kernel_variant(v);
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 0;
+      // two ~100 KB CTAs per SM need the full shared-memory carve-out (the default sizes it for one)
+      cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncAttributes fv{};
+      if (cudaFuncGetAttributes(&fv, fn) != cudaSuccess) return 0;
+      if (fv.numRegs > worst_regs) worst_regs = fv.numRegs;
+      if ((int)fv.sharedSizeBytes > worst_static) worst_static = (int)fv.sharedSizeBytes;
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_api, kernel_variant(0), 256, SMEM_BYTES);
     // Own bound from the hardware limits (shared memory incl. 1 KB/CTA reserved, registers in 8-register
     // warp granules, 512 TMEM columns); the runtime's occupancy answer is taken when it is larger.
     cudaFuncAttributes fa{};
-    if (cudaFuncGetAttributes(&fa, gemm_tc_kernel) != cudaSuccess) return 0;
+    fa.numRegs = worst_regs;
+    fa.sharedSizeBytes = (size_t)worst_static;
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
     const int by_smem = smem_sm / (SMEM_BYTES + 1024 + (int)fa.sharedSizeBytes);
@@ -649,7 +655,6 @@ struct GemmDesc {
   void* out; int out_bf16; int64_t ldo;
   float* out2; int64_t ldo2;
   float* db_out;
-  int pre_a, pre_b;
 };
 
 static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, unsigned long long* counters, float* db_partial,
@@ -681,7 +686,6 @@ static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, unsign
   }
   P->partial = reinterpret_cast<float4*>(partial);
   P->counters = counters;
-  P->pre_a = d.pre_a; P->pre_b = d.pre_b;
   P->db_out = d.db_out; P->db_partial = db_partial;
   return IIF_OK;
 }
@@ -751,7 +755,6 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
     // the grid barrier needs every CTA resident; C <= 4096 with 256 threads per row
     if (cta > cap || loss->C > 4096 || (loss->C & 3) || !loss->scratch) return IIF_EUNSUPPORTED;
     g.fuse_loss = 1;
-    g.loss_prefetch = d[0].pre_b;            // the caller's "inputs are stable" promise
     g.loss_ne = loss->C <= 1024 ? 4 : (loss->C <= 2048 ? 8 : 16);
     g.grid_bar = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + 4096);
     g.loss = *loss;
@@ -769,7 +772,9 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], g);
+  void* kargs[7] = {&maps[0], &maps[1], &maps[2], &maps[3], &maps[4], &maps[5], &g};
+  const int variant = !g.fuse_loss ? 0 : (g.loss_ne == 4 ? 1 : (g.loss_ne == 8 ? 2 : 3));
+  cudaError_t e = cudaLaunchKernelExC(&cfg, kernel_variant(variant), kargs);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return (int)e;
   return IIF_OK;
@@ -779,28 +784,23 @@ static bool bad_dims(int64_t B, int64_t D, int64_t C) {
   return B < 0 || D <= 0 || C <= 0 || B > INT32_MAX || D > INT32_MAX || C > INT32_MAX;
 }
 
-// `stable`: X and W are not written by the launch preceding this one on the stream (see IIF_HEAD_STABLE_OPERANDS)
 static GemmDesc desc_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* cs,
-                         float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B, int64_t D, int64_t C,
-                         bool stable = false) {
+                         float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B, int64_t D, int64_t C) {
   GemmDesc d{};
-  d.pre_a = d.pre_b = stable;
   d.A = x; d.lda = ldx; d.a_mn = false; d.Bm = w; d.ldb = ldw; d.b_mn = false; d.M = B; d.N = C; d.K = D;
   d.bias = bias; d.col_scale = cs; d.out = z; d.out_bf16 = 0; d.ldo = ldz; d.out2 = zs; d.ldo2 = ldzs;
   return d;
 }
 static GemmDesc desc_dx(const void* dz, int64_t lddz, const void* w, int64_t ldw, const float* alpha, void* dx,
-                        int dx_bf16, int64_t lddx, int64_t B, int64_t D, int64_t C, bool stable = false) {
+                        int dx_bf16, int64_t lddx, int64_t B, int64_t D, int64_t C) {
   GemmDesc d{};
-  d.pre_b = stable;
   d.A = dz; d.lda = lddz; d.a_mn = false; d.Bm = w; d.ldb = ldw; d.b_mn = true; d.M = B; d.N = D; d.K = C;
   d.alpha = alpha; d.out = dx; d.out_bf16 = dx_bf16; d.ldo = lddx;
   return d;
 }
 static GemmDesc desc_dw(const void* dz, int64_t lddz, const void* x, int64_t ldx, const float* alpha, float* dw,
-                        int64_t lddw, int64_t B, int64_t D, int64_t C, float* db_out, bool stable = false) {
+                        int64_t lddw, int64_t B, int64_t D, int64_t C, float* db_out) {
   GemmDesc d{};
-  d.pre_b = stable;
   d.A = dz; d.lda = lddz; d.a_mn = true; d.Bm = x; d.ldb = ldx; d.b_mn = true; d.M = C; d.N = D; d.K = B;
   d.alpha = alpha; d.out = dw; d.out_bf16 = 0; d.ldo = lddw;
   d.db_out = db_out;
@@ -822,22 +822,14 @@ extern "C" size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C) {
   return (size_t)WS_HEADER + (size_t)(2 * kNumSMs) * (TILE_M * BN * 4 + TILE_M * 4);
 }
 
-namespace iif {
-int linear_fwd_bf16_ex(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* col_scale,
-                       float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B, int64_t D, int64_t C, void* ws,
-                       size_t ws_bytes, void* stream, bool stable) {
-  if (bad_dims(B, D, C) || !w || (B > 0 && !x) || (!z && !zs) || ldx < D || ldw < D) return IIF_EINVAL;
-  if ((z && ldz < C) || (zs && (ldzs < C || !col_scale))) return IIF_EINVAL;
-  if (B == 0) return IIF_OK;
-  const GemmDesc d = desc_fwd(x, ldx, w, ldw, bias, col_scale, z, ldz, zs, ldzs, B, D, C, stable);
-  return launch_group(&d, 1, ws, ws_bytes, (cudaStream_t)stream);
-}
-}  // namespace iif
-
 extern "C" int iif_linear_fwd_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
                                    const float* col_scale, float* z, int64_t ldz, float* zs, int64_t ldzs, int64_t B,
                                    int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream) {
-  return linear_fwd_bf16_ex(x, ldx, w, ldw, bias, col_scale, z, ldz, zs, ldzs, B, D, C, ws, ws_bytes, stream, false);
+  if (bad_dims(B, D, C) || !w || (B > 0 && !x) || (!z && !zs) || ldx < D || ldw < D) return IIF_EINVAL;
+  if ((z && ldz < C) || (zs && (ldzs < C || !col_scale))) return IIF_EINVAL;
+  if (B == 0) return IIF_OK;
+  const GemmDesc d = desc_fwd(x, ldx, w, ldw, bias, col_scale, z, ldz, zs, ldzs, B, D, C);
+  return launch_group(&d, 1, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int iif_linear_bwd_dx_bf16(const void* dz, int64_t lddz, const void* w, int64_t ldw, const float* alpha_dev,
@@ -862,10 +854,10 @@ extern "C" int iif_linear_bwd_dw_bf16(const void* dz, int64_t lddz, const void* 
   return launch_group(&d, 1, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-namespace iif {
-int linear_bwd_bf16_ex(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
-                       const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw, int64_t lddw, float* db,
-                       int64_t B, int64_t D, int64_t C, void* ws, size_t ws_bytes, void* stream, bool stable) {
+extern "C" int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
+                                   const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw,
+                                   int64_t lddw, float* db, int64_t B, int64_t D, int64_t C, void* ws,
+                                   size_t ws_bytes, void* stream) {
   if (bad_dims(B, D, C) || !dw || (B > 0 && (!dz || !x)) || lddz < C || ldx < D || lddw < D) return IIF_EINVAL;
   if (dx && (!w || ldw < D || lddx < D || (dx_dtype != IIF_DTYPE_F32 && dx_dtype != IIF_DTYPE_BF16))) return IIF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -876,18 +868,9 @@ int linear_bwd_bf16_ex(const void* dz, int64_t lddz, const void* x, int64_t ldx,
   }
   GemmDesc d[2];
   int n = 0;
-  if (dx) d[n++] = desc_dx(dz, lddz, w, ldw, alpha_dev, dx, dx_dtype == IIF_DTYPE_BF16, lddx, B, D, C, stable);
-  d[n++] = desc_dw(dz, lddz, x, ldx, alpha_dev, dw, lddw, B, D, C, db, stable);
+  if (dx) d[n++] = desc_dx(dz, lddz, w, ldw, alpha_dev, dx, dx_dtype == IIF_DTYPE_BF16, lddx, B, D, C);
+  d[n++] = desc_dw(dz, lddz, x, ldx, alpha_dev, dw, lddw, B, D, C, db);
   return launch_group(d, n, ws, ws_bytes, st);
-}
-}  // namespace iif
-
-extern "C" int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int64_t ldx, const void* w, int64_t ldw,
-                                   const float* alpha_dev, void* dx, int dx_dtype, int64_t lddx, float* dw,
-                                   int64_t lddw, float* db, int64_t B, int64_t D, int64_t C, void* ws,
-                                   size_t ws_bytes, void* stream) {
-  return linear_bwd_bf16_ex(dz, lddz, x, ldx, w, ldw, alpha_dev, dx, dx_dtype, lddx, dw, lddw, db, B, D, C, ws, ws_bytes,
-                            stream, false);
 }
 
 static int loss_linear_bwd(const iif_head_args* h, void* stream, bool dry_run) {
@@ -905,10 +888,9 @@ static int loss_linear_bwd(const iif_head_args* h, void* stream, bool dry_run) {
   if (!vec) return IIF_EUNSUPPORTED;
   GemmDesc d[2];
   int n = 0;
-  const bool stable = (h->flags & IIF_HEAD_STABLE_OPERANDS) != 0;
   if (h->dx)
-    d[n++] = desc_dx(h->dz_bf16, h->lddz, h->w, h->ldw, nullptr, h->dx, h->dx_dtype == IIF_DTYPE_BF16, h->lddx, B, D, C, stable);
-  d[n++] = desc_dw(h->dz_bf16, h->lddz, h->x, h->ldx, nullptr, h->dw, h->lddw, B, D, C, h->db, stable);
+    d[n++] = desc_dx(h->dz_bf16, h->lddz, h->w, h->ldw, nullptr, h->dx, h->dx_dtype == IIF_DTYPE_BF16, h->lddx, B, D, C);
+  d[n++] = desc_dw(h->dz_bf16, h->lddz, h->x, h->ldx, nullptr, h->dw, h->lddw, B, D, C, h->db);
   return launch_group(d, n, h->ws, h->ws_bytes, (cudaStream_t)stream, &a, dry_run);
 }
 

@@ -10,6 +10,14 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Cold path of every bounded wait: kept out of line so the hot code stays compact in the instruction cache.
+__device__ __noinline__ static void wait_timed_out(int what) {
+  printf("iif_b200: %s timed out (block %d thread %d)%s\n",
+         what == 0 ? "mbarrier wait" : (what == 1 ? "inter-CTA flag wait" : "split-K rendezvous"), blockIdx.x, threadIdx.x,
+         what == 0 ? "" : ": workspace header not zeroed?");
+  __trap();
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -43,11 +51,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("iif_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000ll) wait_timed_out(0);
   }
 }
 
@@ -123,22 +127,14 @@ __device__ __forceinline__ void spin_until_ge(const int* p, int target) {
   if (ld_acquire(p) >= target) return;
   const long long t0 = clock64();
   while (ld_acquire(p) < target) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("iif_b200: inter-CTA flag wait timed out (block %d thread %d): workspace header not zeroed?\n", blockIdx.x,
-             threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000ll) wait_timed_out(1);
   }
 }
 __device__ __forceinline__ void spin_until_ge_u64(const unsigned long long* p, unsigned long long target) {
   if (ld_acquire_u64(p) >= target) return;
   const long long t0 = clock64();
   while (ld_acquire_u64(p) < target) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("iif_b200: split-K rendezvous timed out (block %d thread %d): workspace header not zeroed?\n", blockIdx.x,
-             threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000ll) wait_timed_out(2);
   }
 }
 

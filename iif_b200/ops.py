@@ -364,7 +364,7 @@ class HeadStep:
     (`grad_flat`) so the data-parallel all-reduce of the head's parameter gradients is one message."""
 
     def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False, ws=None,
-                 fused_loss=True, stable_operands=False):
+                 fused_loss=True):
         dev = torch.device(device)
         self.B, self.D, self.C, self.device = B, D, Cc, dev
         f32, i32 = torch.float32, torch.int32
@@ -387,9 +387,6 @@ class HeadStep:
         self.ws_bytes = n
         self.dx_dtype = _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32
         self.fused_loss = bool(fused_loss)
-        # promise that x / w are not written by the launch preceding each step on the stream (see
-        # IIF_HEAD_STABLE_OPERANDS): lets the GEMMs prefetch them under the previous kernel's tail
-        self.stable_operands = bool(stable_operands)
         self.launches_per_step = 3     # refined by bind(): 2 when the loss rows ride in the backward launch
         self._args = None
         self._keep = None
@@ -432,8 +429,7 @@ class HeadStep:
         a.acc_counts = None if self.acc_counts is None else self.acc_counts.data_ptr()
         a.scratch = self.scratch.data_ptr()
         a.ws, a.ws_bytes = self.ws.data_ptr(), self.ws_bytes
-        a.flags = (0 if self.fused_loss else _lib.HEAD_NO_FUSED_LOSS) | \
-                  (_lib.HEAD_STABLE_OPERANDS if self.stable_operands else 0)
+        a.flags = 0 if self.fused_loss else _lib.HEAD_NO_FUSED_LOSS
         n = int(_lib.load().iif_head_launches(C.byref(a)))
         if n < 0:
             _lib.check(n, "head_launches")

@@ -248,16 +248,11 @@ typedef struct iif_head_args {
  * chained by programmatic dependent launch (cls/train.py:66-77 collapsed to the head;
  * seg/.../bbox_head.py:118 + :269-274 + autograd). */
 #define IIF_HEAD_NO_FUSED_LOSS 1      /* keep the loss rows in their own launch (3 launches per step) */
-/* Caller's promise: x and w are NOT written by the kernel launch that immediately precedes this call on
- * `stream` (true for a training loop whose previous launch on the stream is this library's own backward,
- * or whose inputs arrive by copies / events).  The GEMM kernels then request their x / w tiles before the
- * programmatic-dependency wait, hiding the HBM latency under the predecessor's tail. */
-#define IIF_HEAD_STABLE_OPERANDS 2
 IIF_API int iif_head_fwd_bwd_bf16(const iif_head_args* args, void* stream);
 /* The loss rows + AddmmBackward in ONE launch: every CTA of the backward launch first computes its share
  * of the softmax-CE rows (reads args->z, writes loss_i / dz_bf16 / argmax / rank), the grid meets at a
  * counter in the workspace header, then dX, dW, db are formed from dZ out of L2.  The X / W operand tiles
- * are requested before the loss rows run.  Returns IIF_EUNSUPPORTED (nothing launched) when the shape
+ * are requested before the loss rows run (after the programmatic-dependency wait).  Returns IIF_EUNSUPPORTED (nothing launched) when the shape
  * does not qualify: grid above the resident-CTA capacity, C > 4096 or C % 4 != 0, unaligned rows. */
 IIF_API int iif_loss_linear_bwd_bf16(const iif_head_args* args, void* stream);
 /* Number of launches iif_head_fwd_bwd_bf16 makes for these arguments (2 or 3); negative = argument error. */

@@ -44,14 +44,12 @@ show("bwd group", lambda: ops.linear_bwd(dz, x, w, dx_bf16=True))
 show("dw only", lambda: ops.linear_bwd(dz, x, w, need_dx=False))
 y = torch.randint(0, C, (B,), device=dev)
 iif = torch.rand(C, device=dev) * 6 + 0.5
-for stable in (False, True):
-    hs = ops.HeadStep(B, D, C, dev, stable_operands=stable)
-    hs.bind(x, w, bias, iif, y)
-    k = dict(hs.kernels())
-    hs.launch(); torch.cuda.synchronize()
-    if "loss_linear_bwd_bf16" in k:
-        show(f"loss+bwd fused (stable_operands={stable})", k["loss_linear_bwd_bf16"])
-    show(f"fwd via head (stable_operands={stable})", k["linear_fwd_bf16"])
+hs = ops.HeadStep(B, D, C, dev)
+hs.bind(x, w, bias, iif, y)
+k = dict(hs.kernels())
+hs.launch(); torch.cuda.synchronize()
+if "loss_linear_bwd_bf16" in k:
+    show("loss+bwd fused", k["loss_linear_bwd_bf16"])
 for i in range(3):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(); ops.linear_fwd(x, w, bias); t1.record(); torch.cuda.synchronize()
