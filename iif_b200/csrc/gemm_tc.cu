@@ -62,12 +62,16 @@ constexpr int BN = 128;
 constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * TILE_K * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 6;          // 1 CTA / SM (grids that fit one wave of 148 CTAs): deeper TMA ring
+constexpr int MIN_STAGES = 3;          // 2 CTAs / SM
 constexpr int MAX_SPLITS = 8;
 constexpr int ONES_BYTES = 2048;      // 16 rows x 128 B of bf16 1.0 (K-major B operand of the db MMA)
 constexpr int TMEM_COLS = 256;        // BN accumulator columns + 16 for db (power of two)
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + BAR_BYTES + 2 * BN * 4 + 1024;
+__host__ __device__ constexpr int smem_bytes_for(int stages) {
+  return stages * STAGE_BYTES + ONES_BYTES + BAR_BYTES + 2 * BN * 4 + 1024;
+}
+constexpr int SMEM_BYTES = smem_bytes_for(MIN_STAGES);       // the 2-CTAs-per-SM configuration
 constexpr int GEN_PITCH = 65;         // generic epilogue: warp-private 32 x 65 float slab
 constexpr int WS_HEADER = 8192;       // split-K counters: 2 problems x 256 tiles x {arrive, done}; grid barrier at 4096
 constexpr int TILE_F4 = TILE_M * BN / 4;
@@ -75,8 +79,8 @@ constexpr int TILE_F4 = TILE_M * BN / 4;
 // advances the tile's counter by exactly EPOCH_UNIT whatever its split count (840 = lcm(1..8)); the
 // value an arriver gets back tells it which multiple to wait for.  64-bit: no wrap in practice.
 constexpr unsigned long long EPOCH_UNIT = 840;
-static_assert(8 * 32 * GEN_PITCH * 4 <= STAGES * STAGE_BYTES, "generic staging must fit in the stage ring");
-static_assert(TILE_M * BN * 4 <= STAGES * STAGE_BYTES, "TMA-store staging must fit in the stage ring");
+static_assert(8 * 32 * GEN_PITCH * 4 <= MIN_STAGES * STAGE_BYTES, "generic staging must fit in the stage ring");
+static_assert(TILE_M * BN * 4 <= MIN_STAGES * STAGE_BYTES, "TMA-store staging must fit in the stage ring");
 
 struct TcProblem {
   int M, N, K;
@@ -91,7 +95,7 @@ struct TcProblem {
 };
 
 struct TcGroup {
-  int nprob;
+  int nprob, stages;
   int cta_begin[3];
   long long* dbg;                        // optional per-CTA phase timestamps (iif_debug_timing)
   TcProblem p[2];
@@ -158,12 +162,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int STAGES = g.stages;
   const uint32_t ones_base = smem_base + STAGES * STAGE_BYTES;      // 1024-byte aligned
   const uint32_t bar_base = ones_base + ONES_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   float* s_bias = reinterpret_cast<float*>(smem_gen + (bar_base + BAR_BYTES - smem_base));
   float* s_scale = s_bias + BN;
@@ -245,7 +250,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   double loss_part = 0.0;
   int loss_c1 = 0, loss_c5 = 0;
   if constexpr (FUSE_NE != 0) {
-    // ---- loss-fused launch: B operands (X / W tiles: independent of the loss) are requested first ...
+    // ---- loss-fused launch: B operands (X / W tiles: independent of the loss) are requested first (measured:
+    // requesting them after the rows, around the grid barrier, slows the barrier's polls down by as much) ...
     if (threadIdx.x == 0)
       for (int i = 0; i < n_first; ++i) load_b(i, kb_begin + i);
     // ---- ... then every CTA computes its share of the loss rows: Z -> loss_i, dZ (bf16, global)
@@ -582,7 +588,8 @@ static int resident_capacity(int* detail = nullptr) {
     int worst_regs = 0, worst_static = 0;
     for (int v = 0; v < 4; ++v) {
       const void* fn = kernel_variant(v);
-      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 0;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(MAX_STAGES)) != cudaSuccess)
+        return 0;
       // two ~100 KB CTAs per SM need the full shared-memory carve-out (the default sizes it for one)
       cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       cudaFuncAttributes fv{};
@@ -751,6 +758,14 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
   g.cta_begin[nprob] = cta;
   g.nprob = nprob;
   g.dbg = g_dbg;
+  // one wave of at most one CTA per SM: give each CTA the whole SM's shared memory (deeper TMA ring, more
+  // bytes in flight per CTA); larger grids run two ~100 KB CTAs per SM
+  int kb_max = 1;
+  for (int i = 0; i < nprob; ++i) if (plans[i].kb_per_split > kb_max) kb_max = plans[i].kb_per_split;
+  g.stages = MIN_STAGES;
+  // (measured: for the 4-k-block CTAs of the head shapes a deeper ring only delays the first stage -- the
+  // cold HBM fetch is not limited by bytes in flight per CTA; long unsplit K loops of a single-wave grid do use it)
+  if (cta <= cap / 2 && !loss && kb_max >= 2 * MAX_STAGES) g.stages = MAX_STAGES;
   if (loss) {
     // the grid barrier needs every CTA resident; C <= 4096 with 256 threads per row
     if (cta > cap || loss->C > 4096 || (loss->C & 3) || !loss->scratch) return IIF_EUNSUPPORTED;
@@ -765,7 +780,7 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)cta);
   cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes_for(g.stages);
   cfg.stream = st;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
