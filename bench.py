@@ -49,6 +49,11 @@ def parse():
     ap.add_argument("--no-fused-loss", action="store_true", help="3 launches per step (loss rows in their own launch)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--sync-allreduce", action="store_true", help="N>1: all-reduce on the compute stream (no overlap)")
+    ap.add_argument("--ar-ctas", type=int, default=0)
+    ap.add_argument("--ar-threads", type=int, default=0)
+    ap.add_argument("--py-loop", action="store_true", help="N>1: drive steps + all-reduce from Python (graph replay) instead of the C pipeline")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "peer-nomc", "nccl"],
+                    help="N>1: the library's NVLink peer-memory kernel (with / without NVLS multicast) or NCCL")
     return ap.parse_args()
 
 
@@ -177,6 +182,13 @@ def main():
     S = max(2, int(-(-2.0 * L2_BYTES // per_set)))           # rotating sets: footprint >= 2 x L2
     prob = torch.from_numpy(cnt / cnt.sum())
     sets = []
+    peer = None
+    ar_kind = "nccl"
+    if world > 1 and args.allreduce != "nccl":
+        from iif_b200.parallel import PeerAllReduce
+        peer = PeerAllReduce(C * D + C, S, dev, use_multicast=(args.allreduce == "peer"), num_ctas=args.ar_ctas,
+                             num_threads=args.ar_threads)
+        ar_kind = "peer-memory kernel" + (" (NVLS multimem)" if peer.multicast else " (peer loads/stores)")
     shared_ws = torch.zeros(max(int(ops._lib.load().iif_gemm_ws_bytes(B, D, C)), 1), dtype=torch.uint8, device=dev)
     for s in range(S):
         x = torch.randn(B, D, generator=g).to(dev).to(torch.bfloat16)
@@ -184,7 +196,7 @@ def main():
         y = torch.multinomial(prob, B, replacement=True, generator=g).to(dev)
         bias = torch.full((C,), 0.01, device=dev)
         hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws,
-                          fused_loss=not args.no_fused_loss)
+                          fused_loss=not args.no_fused_loss, grad_flat=None if peer is None else peer.buffer(s))
         hs.bind(x, w, bias, iif, y)
         sets.append(hs)
     launches_per_step = sets[0].launches_per_step
@@ -210,6 +222,13 @@ def main():
             graphs[i] = gph
         torch.cuda.synchronize(dev)
 
+    def all_reduce(k, stream):
+        if peer is not None:
+            peer.all_reduce(k, stream)
+        else:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
+
     def step(i):
         k = i % S
         if world > 1 and ar_done[k] is not None:
@@ -220,35 +239,58 @@ def main():
             sets[k].launch()
         if world > 1:
             if args.sync_allreduce:
-                dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
+                all_reduce(k, cur)
             else:
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 comm.wait_event(ev)
-                with torch.cuda.stream(comm):
-                    dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
-                    done = torch.cuda.Event()
-                    done.record(comm)
+                all_reduce(k, comm)
+                done = torch.cuda.Event()
+                done.record(comm)
                 ar_done[k] = done
 
+    # N > 1 with the peer-memory all-reduce: the whole loop runs through the C pipeline (one call per step
+    # enqueues the step on its compute stream and the all-reduce of its gradients on its comm stream), so
+    # the host is not the bottleneck of a 30 us step; events are recorded on the pipeline's own streams.
+    pipe_main = None
+    if world > 1 and peer is not None and not args.sync_allreduce and not args.py_loop:
+        pipe_main = ops.HeadPipeline(sets)
+        pipe_main.set_allreduce(peer)
+        _, p_compute, _, p_comm = pipe_main.streams()
+        use_graph = False
+
+    def run_steps(n):
+        if pipe_main is not None:
+            for i in range(n):
+                pipe_main.submit_device(i % S)
+        else:
+            for i in range(n):
+                step(i)
+
     def fence():
+        if pipe_main is not None:
+            pipe_main.sync()
         if world > 1:
             cur.wait_stream(comm)
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    run_steps(max(args.warmup, 3))
     fence()
     n0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        e0.record(cur)
-        for i in range(args.steps):
-            step(i)
-        if world > 1:
-            cur.wait_stream(comm)
-        e1.record(cur)
+        if pipe_main is not None:
+            e0.record(p_compute)
+            run_steps(args.steps)
+            p_comm.wait_stream(p_compute)       # the last all-reduce is ordered after the last step anyway
+            e1.record(p_comm)
+        else:
+            e0.record(cur)
+            run_steps(args.steps)
+            if world > 1:
+                cur.wait_stream(comm)
+            e1.record(cur)
         fence()
     ms = e0.elapsed_time(e1)
     if world > 1:
@@ -266,7 +308,11 @@ def main():
     # next batch's PCIe copy overlaps the current step's kernels.  Wall clock, synchronised both sides.
     hx = [torch.randn(B, D, generator=g).to(torch.bfloat16).pin_memory() for _ in range(4)]
     hy = [torch.multinomial(prob, B, replacement=True, generator=g).pin_memory() for _ in range(4)]
+    if pipe_main is not None:
+        pipe_main.close()
     pipe = ops.HeadPipeline(sets)
+    if world > 1 and peer is not None:
+        pipe.set_allreduce(peer)
     lag = 4
     e2e_loss = [0.0]
 
@@ -276,10 +322,9 @@ def main():
             if i >= lag:
                 e2e_loss[0] = pipe.wait((i - lag) % S)          # device -> host read of step i-lag's loss
             pipe.submit(k, hx[i % 4], hy[i % 4])
-            if world > 1:
+            if world > 1 and peer is None:
                 pipe.stream_wait_step(k, comm)
-                with torch.cuda.stream(comm):
-                    dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
+                all_reduce(k, comm)
                 pipe.hold_slot(k, comm)
         for i in range(max(n - lag, 0), n):
             e2e_loss[0] = pipe.wait(i % S)
@@ -366,11 +411,12 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD if (B, D, C) == (256, 2048, 1000) else f"IIF head {B}x{D}x{C}",
                            "B_per_gpu": B, "D": D, "C": C, "global_batch": B * world, "variant": args.variant,
-                           "parallelism": f"dp{world} (row sharding, NCCL all-reduce(mean) of dW+db "
+                           "parallelism": f"dp{world} (row sharding, {ar_kind} all-reduce(mean) of dW+db "
                                           f"{'on the compute stream' if args.sync_allreduce else 'overlapped on a side stream'})"
                                           if world > 1 else "dp1",
                            "launch": (f"cuda-graph replay (one graph = the {launches_per_step} launches of a step)"
-                                      if use_graph else "eager"),
+                                      if use_graph else ("eager, one C call per step (iif_pipeline_submit_device)"
+                                                         if pipe_main is not None else "eager")),
                            "l2": f"rotating {S} independent input+output sets, {S * per_set / 1e6:.0f} MB > 126 MB L2"},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
                 "kernels": kern, "cpu_baseline": cpu, "loss": loss_val}

@@ -698,12 +698,17 @@ static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, unsign
 }
 
 static long long* g_dbg = nullptr;   // iif_debug_timing
+static std::atomic<int> g_reserved_slots{0};   // iif_gemm_reserve_slots
 
 // Launch one or two problems in one grid.
 static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes, cudaStream_t st,
                         const RowArgs* loss = nullptr, bool dry_run = false) {
-  const int cap = resident_capacity();
+  int cap = resident_capacity();
   if (cap <= 0) { cudaGetLastError(); return IIF_EDRIVER; }
+  // resident-CTA slots promised to kernels that overlap these launches AND block on other GPUs (the
+  // all-reduce): the in-kernel rendezvous may only count on the rest
+  cap -= g_reserved_slots.load(std::memory_order_relaxed);
+  if (cap < 1) cap = 1;
   TcGroup g{};
   CUtensorMap maps[6] = {};
   Plan plans[2];
@@ -827,6 +832,11 @@ static GemmDesc desc_dw(const void* dz, int64_t lddz, const void* x, int64_t ldx
 using namespace iif;
 
 extern "C" void iif_debug_timing(long long* buf) { g_dbg = buf; }
+extern "C" int iif_gemm_reserve_slots(int slots) {
+  if (slots < 0) return IIF_EINVAL;
+  g_reserved_slots.store(slots, std::memory_order_relaxed);
+  return IIF_OK;
+}
 extern "C" int iif_debug_capacity(int* detail6) { return resident_capacity(detail6); }
 
 extern "C" size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C) {

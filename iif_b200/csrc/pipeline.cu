@@ -15,10 +15,16 @@ struct iif_pipeline {
     iif_head_args a;
     cudaEvent_t h2d_done, step_done, loss_done, release;
     bool used, held;
+    int64_t ar_offset;
   };
   int nslots;
-  cudaStream_t s_h2d, s_compute, s_d2h;
+  cudaStream_t s_h2d, s_compute, s_d2h, s_comm;
   Slot* slots;
+  // optional data-parallel exchange after every step (iif_pipeline_set_allreduce)
+  bool ar_on;
+  void* const* ar_bufs; void* const* ar_flags; void* ar_mc;
+  int ar_rank, ar_world, ar_ctas, ar_threads;
+  int64_t ar_n;
 };
 
 #define IIF_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
@@ -39,6 +45,11 @@ extern "C" int iif_pipeline_create(iif_pipeline** out, const iif_head_args* slot
   IIF_CU(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
   IIF_CU(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
   IIF_CU(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+  {  // the all-reduce gates the reuse of gradient buffers: let its CTAs be scheduled ahead of queued GEMM CTAs
+    int lo = 0, hi = 0;
+    IIF_CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    IIF_CU(cudaStreamCreateWithPriority(&p->s_comm, cudaStreamNonBlocking, hi));
+  }
   for (int i = 0; i < nslots; ++i) {
     iif_pipeline::Slot& s = p->slots[i];
     s.a = slot_args[i];
@@ -51,6 +62,33 @@ extern "C" int iif_pipeline_create(iif_pipeline** out, const iif_head_args* slot
   return IIF_OK;
 }
 
+extern "C" int iif_pipeline_set_allreduce(iif_pipeline* p, void* const* peer_bufs_dev, void* const* peer_flags_dev,
+                                          void* multicast_ptr, int rank, int world, const int64_t* slot_offsets_elems,
+                                          int64_t n_elems, int num_ctas, int num_threads) {
+  if (!p || !peer_bufs_dev || !peer_flags_dev || !slot_offsets_elems || world < 1 || rank < 0 || rank >= world) return IIF_EINVAL;
+  p->ar_bufs = peer_bufs_dev; p->ar_flags = peer_flags_dev; p->ar_mc = multicast_ptr;
+  p->ar_rank = rank; p->ar_world = world; p->ar_n = n_elems; p->ar_ctas = num_ctas; p->ar_threads = num_threads;
+  for (int i = 0; i < p->nslots; ++i) p->slots[i].ar_offset = slot_offsets_elems[i];
+  p->ar_on = world > 1;
+  return IIF_OK;
+}
+
+// the step on the compute stream, then (data-parallel runs) the all-reduce of its gradients on the comm stream
+static int run_step(iif_pipeline* p, iif_pipeline::Slot& s) {
+  if (s.held) { IIF_CU(cudaStreamWaitEvent(p->s_compute, s.release, 0)); s.held = false; }  // gradients still in flight
+  if (int rc = iif_head_fwd_bwd_bf16(&s.a, p->s_compute)) return rc;
+  IIF_CU(cudaEventRecord(s.step_done, p->s_compute));
+  if (p->ar_on) {
+    IIF_CU(cudaStreamWaitEvent(p->s_comm, s.step_done, 0));
+    if (int rc = iif_allreduce_mean_f32(p->ar_bufs, p->ar_flags, p->ar_mc, p->ar_rank, p->ar_world, s.ar_offset, p->ar_n,
+                                        p->ar_ctas, p->ar_threads, p->s_comm))
+      return rc;
+    IIF_CU(cudaEventRecord(s.release, p->s_comm));
+    s.held = true;
+  }
+  return IIF_OK;
+}
+
 extern "C" int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x, const int64_t* host_label,
                                    float* host_loss) {
   if (!p || slot < 0 || slot >= p->nslots || !host_x || !host_label || !host_loss) return IIF_EINVAL;
@@ -58,7 +96,6 @@ extern "C" int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x
   const iif_head_args& a = s.a;
   // the slot's device buffers are free once its previous step (and whoever held its gradients) is done
   if (s.used) IIF_CU(cudaStreamWaitEvent(p->s_h2d, s.loss_done, 0));
-  if (s.held) { IIF_CU(cudaStreamWaitEvent(p->s_h2d, s.release, 0)); s.held = false; }
   if (a.ldx == a.D)
     IIF_CU(cudaMemcpyAsync(const_cast<void*>(a.x), host_x, (size_t)a.B * a.D * 2, cudaMemcpyHostToDevice, p->s_h2d));
   else
@@ -67,12 +104,26 @@ extern "C" int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x
   IIF_CU(cudaMemcpyAsync(const_cast<int64_t*>(a.label), host_label, (size_t)a.B * 8, cudaMemcpyHostToDevice, p->s_h2d));
   IIF_CU(cudaEventRecord(s.h2d_done, p->s_h2d));
   IIF_CU(cudaStreamWaitEvent(p->s_compute, s.h2d_done, 0));
-  if (int rc = iif_head_fwd_bwd_bf16(&a, p->s_compute)) return rc;
-  IIF_CU(cudaEventRecord(s.step_done, p->s_compute));
+  if (int rc = run_step(p, s)) return rc;
   IIF_CU(cudaStreamWaitEvent(p->s_d2h, s.step_done, 0));
   IIF_CU(cudaMemcpyAsync(host_loss, a.loss_sum, 4, cudaMemcpyDeviceToHost, p->s_d2h));
   IIF_CU(cudaEventRecord(s.loss_done, p->s_d2h));
   s.used = true;
+  return IIF_OK;
+}
+
+// Same step with the inputs ALREADY in the slot's device buffers (no copies): the device-resident loop.
+extern "C" int iif_pipeline_submit_device(iif_pipeline* p, int slot) {
+  if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  return run_step(p, p->slots[slot]);
+}
+
+extern "C" int iif_pipeline_get_streams(iif_pipeline* p, void** h2d, void** compute, void** d2h, void** comm) {
+  if (!p) return IIF_EINVAL;
+  if (h2d) *h2d = p->s_h2d;
+  if (compute) *compute = p->s_compute;
+  if (d2h) *d2h = p->s_d2h;
+  if (comm) *comm = p->s_comm;
   return IIF_OK;
 }
 
@@ -90,7 +141,7 @@ extern "C" int iif_pipeline_stream_wait_step(iif_pipeline* p, int slot, void* st
 }
 
 extern "C" int iif_pipeline_hold_slot(iif_pipeline* p, int slot, void* stream) {
-  if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  if (!p || slot < 0 || slot >= p->nslots || p->ar_on) return IIF_EINVAL;   // with a built-in all-reduce the pipeline holds slots itself
   IIF_CU(cudaEventRecord(p->slots[slot].release, (cudaStream_t)stream));
   p->slots[slot].held = true;
   return IIF_OK;
@@ -101,6 +152,7 @@ extern "C" int iif_pipeline_sync(iif_pipeline* p) {
   IIF_CU(cudaStreamSynchronize(p->s_h2d));
   IIF_CU(cudaStreamSynchronize(p->s_compute));
   IIF_CU(cudaStreamSynchronize(p->s_d2h));
+  IIF_CU(cudaStreamSynchronize(p->s_comm));
   return IIF_OK;
 }
 
@@ -116,6 +168,7 @@ extern "C" void iif_pipeline_destroy(iif_pipeline* p) {
   cudaStreamDestroy(p->s_h2d);
   cudaStreamDestroy(p->s_compute);
   cudaStreamDestroy(p->s_d2h);
+  cudaStreamDestroy(p->s_comm);
   delete[] p->slots;
   delete p;
 }

@@ -11,7 +11,7 @@ namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Cold path of every bounded wait: kept out of line so the hot code stays compact in the instruction cache.
-__device__ __noinline__ static void wait_timed_out(int what) {
+__device__ __noinline__ inline void wait_timed_out(int what) {
   printf("iif_b200: %s timed out (block %d thread %d)%s\n",
          what == 0 ? "mbarrier wait" : (what == 1 ? "inter-CTA flag wait" : "split-K rendezvous"), blockIdx.x, threadIdx.x,
          what == 0 ? "" : ": workspace header not zeroed?");

@@ -364,7 +364,7 @@ class HeadStep:
     (`grad_flat`) so the data-parallel all-reduce of the head's parameter gradients is one message."""
 
     def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False, ws=None,
-                 fused_loss=True):
+                 fused_loss=True, grad_flat=None):
         dev = torch.device(device)
         self.B, self.D, self.C, self.device = B, D, Cc, dev
         f32, i32 = torch.float32, torch.int32
@@ -373,7 +373,11 @@ class HeadStep:
         self.loss = torch.zeros((), dtype=f32, device=dev)
         self.dz = torch.empty(B, pad8(Cc), dtype=torch.bfloat16, device=dev)
         self.dx = torch.empty(B, D, dtype=torch.bfloat16 if dx_bf16 else f32, device=dev) if need_dx else None
-        self.grad_flat = torch.empty(Cc * D + (Cc if need_db else 0), dtype=f32, device=dev)
+        ng = Cc * D + (Cc if need_db else 0)
+        if grad_flat is not None:      # caller-owned storage (e.g. a peer-mapped buffer of parallel.PeerAllReduce)
+            if grad_flat.dtype != f32 or grad_flat.numel() != ng or not grad_flat.is_contiguous() or not grad_flat.is_cuda:
+                raise ValueError(f"grad_flat must be a contiguous fp32 CUDA tensor of {ng} elements")
+        self.grad_flat = grad_flat if grad_flat is not None else torch.empty(ng, dtype=f32, device=dev)
         self.dw = self.grad_flat[:Cc * D].view(Cc, D)
         self.db = self.grad_flat[Cc * D:] if need_db else None
         self.argmax = torch.empty(B, dtype=i32, device=dev) if want_acc else None
@@ -508,6 +512,32 @@ class HeadPipeline:
         if rc:
             _lib.check(rc, "pipeline_submit")
 
+    def submit_device(self, slot: int) -> None:
+        """The step on the slot's current device buffers (no copies)."""
+        rc = self._lib.iif_pipeline_submit_device(self._h, slot)
+        if rc:
+            _lib.check(rc, "pipeline_submit_device")
+
+    def set_allreduce(self, peer) -> None:
+        """Data-parallel runs: all-reduce(mean) every step's gradients with `peer` (parallel.PeerAllReduce whose
+        buffer(i) is slot i's grad_flat) on the pipeline's comm stream, overlapping the following steps."""
+        n = len(self.steps)
+        for i, hs in enumerate(self.steps):
+            if hs.grad_flat.data_ptr() != peer.buffer(i).data_ptr():
+                raise ValueError("slot gradients must live in the PeerAllReduce buffers (HeadStep(grad_flat=peer.buffer(i)))")
+        offs = (C.c_int64 * n)(*[i * peer.stride for i in range(n)])
+        self._peer = peer
+        _lib.check(self._lib.iif_pipeline_set_allreduce(self._h, peer._bufs, peer._flags, peer._mc, peer.rank, peer.world,
+                                                        offs, (peer.numel + 3) // 4 * 4, peer.num_ctas, peer.num_threads),
+                   "pipeline_set_allreduce")
+
+    def streams(self):
+        """(h2d, compute, d2h, comm) as torch ExternalStreams (to record timing events on them)."""
+        ptrs = [C.c_void_p() for _ in range(4)]
+        _lib.check(self._lib.iif_pipeline_get_streams(self._h, *[C.byref(p) for p in ptrs]), "pipeline_get_streams")
+        dev = self.steps[0].device
+        return tuple(torch.cuda.ExternalStream(p.value, device=dev) for p in ptrs)
+
     def wait(self, slot: int) -> float:
         rc = self._lib.iif_pipeline_wait(self._h, slot)
         if rc:
@@ -522,7 +552,8 @@ class HeadPipeline:
         _lib.check(self._lib.iif_pipeline_hold_slot(self._h, slot, C.c_void_p(stream.cuda_stream)), "pipeline_hold_slot")
 
     def sync(self) -> None:
-        _lib.check(self._lib.iif_pipeline_sync(self._h), "pipeline_sync")
+        if self._h:
+            _lib.check(self._lib.iif_pipeline_sync(self._h), "pipeline_sync")
 
     def close(self) -> None:
         if self._h:

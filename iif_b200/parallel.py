@@ -5,12 +5,18 @@ weights, W / b / iif are replicated, the loss normaliser is LOCAL (mean over the
 classification/custom.py:32-33; local avg_factor, mmdet bbox_head.py:267) and DDP then AVERAGES
 the parameter gradients over ranks (classification/train.py:231-234; mmdet apis/train.py:81-85).
 The only exchange is therefore one all-reduce(mean) of dW [C,D] + db [C] -- kept in one flat fp32
-buffer (`ops.HeadStep.grad_flat`) so it is a single NCCL message over NVLink / NVSwitch.
-`torch.distributed` is the transport (nccl on GPUs; gloo in the CPU tests).
+buffer (`ops.HeadStep.grad_flat`).  Two transports:
+  * `PeerAllReduce`: the library's own one-pass kernel over NVLink peer memory (csrc/allreduce.cu:
+    reduce-scatter + all-gather fused, NVLS multimem when a multicast mapping exists); symmetric memory
+    from torch.distributed._symmetric_memory is only the allocator / rendezvous;
+  * `allreduce_mean_`: torch.distributed (nccl on GPUs -- the baseline the kernel is measured against;
+    gloo in the CPU tests).
 """
 from __future__ import annotations
 
 from typing import Optional, Tuple
+
+import ctypes as C
 
 import torch
 import torch.distributed as dist
@@ -71,3 +77,60 @@ class GradReducer:
         if self._done is not None:
             torch.cuda.current_stream(self.device).wait_event(self._done)
             self._done = None
+
+
+class PeerAllReduce:
+    """`nbuf` flat fp32 gradient buffers in symmetric (peer-mapped) memory + the library's all-reduce(mean)
+    kernel (iif_allreduce_mean_f32).  `buffer(i)` is handed to `ops.HeadStep(grad_flat=...)`; `all_reduce(i,
+    stream)` enqueues the collective for buffer i on `stream` (every rank, same order).
+
+    Raises RuntimeError when symmetric memory cannot be set up (no NVLink peer access, single process
+    without a group): callers fall back to `allreduce_mean_` explicitly -- never silently."""
+
+    def __init__(self, numel: int, nbuf: int, device, group=None, use_multicast: bool = True, num_ctas: int = 0,
+                 num_threads: int = 0):
+        from . import _lib
+        import torch.distributed._symmetric_memory as symm_mem
+        if not dist.is_initialized():
+            raise RuntimeError("PeerAllReduce needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = torch.device(device)
+        self.numel = int(numel)
+        self.stride = (self.numel + 63) // 64 * 64           # 256-byte aligned slots
+        self.nbuf = int(nbuf)
+        self._lib = _lib.load()
+        self._check = _lib.check
+        self.num_ctas = int(num_ctas) if num_ctas else 16
+        self.num_threads = int(num_threads) if num_threads else 256
+        # The all-reduce overlaps the next step's GEMM launches and blocks on other GPUs: keep its footprint
+        # out of the resident-CTA budget their in-kernel rendezvous rely on (include/iif_b200.h).
+        self._check(self._lib.iif_gemm_reserve_slots(self.num_ctas * (1 if self.num_threads <= 256 else 2)),
+                    "gemm_reserve_slots")
+        try:
+            self.mem = symm_mem.empty(self.nbuf * self.stride, dtype=torch.float32, device=self.device)
+            self.mem.zero_()
+            self.hdl = symm_mem.rendezvous(self.mem, self.group)
+            nflag = int(self._lib.iif_allreduce_flag_bytes()) // 4
+            self.flags = symm_mem.empty(nflag, dtype=torch.int32, device=self.device)
+            self.flags.zero_()
+            self.fhdl = symm_mem.rendezvous(self.flags, self.group)
+        except Exception as e:  # noqa: BLE001 - surfaced, not swallowed
+            raise RuntimeError(f"PeerAllReduce: symmetric memory unavailable ({type(e).__name__}: {e})") from e
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)               # every rank's flags are zero before anyone signals
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.multicast = bool(mc) and use_multicast
+        self._mc = C.c_void_p(mc if self.multicast else 0)
+        self._bufs = C.c_void_p(int(self.hdl.buffer_ptrs_dev))
+        self._flags = C.c_void_p(int(self.fhdl.buffer_ptrs_dev))
+
+    def buffer(self, i: int) -> torch.Tensor:
+        return self.mem[i * self.stride: i * self.stride + self.numel]
+
+    def all_reduce(self, i: int, stream: torch.cuda.Stream) -> None:
+        n = (self.numel + 3) // 4 * 4           # the slot is padded: reduce whole float4s
+        rc = self._lib.iif_allreduce_mean_f32(self._bufs, self._flags, self._mc, self.rank, self.world, i * self.stride, n,
+                                              self.num_ctas, self.num_threads, C.c_void_p(stream.cuda_stream))
+        if rc:
+            self._check(rc, "allreduce_mean_f32")

@@ -209,7 +209,16 @@ IIF_API int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int
  * it off.  iif_debug_capacity: resident-CTA capacity of the current device for the tensor-core kernel
  * (the split-K rendezvous is only enabled for grids that fit it). */
 IIF_API void iif_debug_timing(long long* buf);
+IIF_API void iif_debug_timing_allreduce(long long* buf);   /* 8 int64 per CTA: start, after handshake, after data, end */
 IIF_API int iif_debug_capacity(int* detail6 /* host, optional: occupancy API, by smem, by regs, regs, smem/SM, static smem */);
+
+/* Split-K and the loss-fused backward launch rendezvous INSIDE a grid, which is only safe while every CTA
+ * of the grid can be resident at once.  A kernel that overlaps these launches and itself blocks on other
+ * GPUs (iif_allreduce_mean_f32) must not be able to starve them of resident-CTA slots: reserve its
+ * footprint here (1 slot per CTA of <= 256 threads, 2 per larger CTA; process-wide, default 0) and the
+ * planner only counts on the remaining slots (falling back to unsplit / unfused launches when a grid no
+ * longer fits). */
+IIF_API int iif_gemm_reserve_slots(int slots);
 
 /* Workspace (bytes) the three bf16 GEMMs of a head of this shape may need (max over the three). */
 IIF_API size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C);
@@ -273,6 +282,16 @@ IIF_API int iif_pipeline_create(iif_pipeline** out, const iif_head_args* slot_ar
  * contiguous, host_label: [B] int64, host_loss: 4 bytes; all three should be pinned. Never blocks. */
 IIF_API int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x, const int64_t* host_label,
                                 float* host_loss);
+/* The same step with the inputs already in the slot's device buffers (no copies, no loss read-back). */
+IIF_API int iif_pipeline_submit_device(iif_pipeline* p, int slot);
+/* Data-parallel runs: after every step, all-reduce(mean) the slot's gradient slice with
+ * iif_allreduce_mean_f32 on the pipeline's comm stream (arguments as there; slot i's slice starts at
+ * slot_offsets_elems[i]); the slot is not reused before its all-reduce has finished. */
+IIF_API int iif_pipeline_set_allreduce(iif_pipeline* p, void* const* peer_bufs_dev, void* const* peer_flags_dev,
+                                       void* multicast_ptr, int rank, int world, const int64_t* slot_offsets_elems,
+                                       int64_t n_elems, int num_ctas, int num_threads);
+/* The pipeline's streams (cudaStream_t), e.g. to record timing events on them; any pointer may be NULL. */
+IIF_API int iif_pipeline_get_streams(iif_pipeline* p, void** h2d, void** compute, void** d2h, void** comm);
 /* Block until the slot's latest step has delivered its loss to host_loss. */
 IIF_API int iif_pipeline_wait(iif_pipeline* p, int slot);
 /* Make `stream` wait for the slot's latest step (its gradients are then complete) ... */
@@ -282,6 +301,24 @@ IIF_API int iif_pipeline_stream_wait_step(iif_pipeline* p, int slot, void* strea
 IIF_API int iif_pipeline_hold_slot(iif_pipeline* p, int slot, void* stream);
 IIF_API int iif_pipeline_sync(iif_pipeline* p);
 IIF_API void iif_pipeline_destroy(iif_pipeline* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * (e) all-reduce(mean) of the flat fp32 gradient buffer [dW | db] over NVLink peer memory
+ * (replaces the DDP bucket all-reduce of fc.weight.grad / fc.bias.grad: cls/train.py:231-234,
+ * seg/mmdet/apis/train.py:81-85; mean over ranks = DDP semantics).
+ *   peer_bufs_dev  : DEVICE array [world] of the ranks' buffer base pointers (symmetric memory: every
+ *                    rank's buffer is mapped into every process; same offset on every rank)
+ *   peer_flags_dev : DEVICE array [world] of the ranks' flag arrays, iif_allreduce_flag_bytes() each,
+ *                    ZERO when first used (monotonic launch counters; never reset them afterwards)
+ *   multicast_ptr  : NVLS multicast mapping of the buffer, or NULL (then plain peer loads / stores)
+ *   offset_elems, n_elems : the slice of the buffer to reduce, both multiples of 4
+ * Collective: every rank must launch it with the same arguments (its own rank aside), stream-ordered
+ * after the rank's own writes to the slice.  In place; the result is bit-identical on every rank.
+ * ------------------------------------------------------------------------------------------- */
+IIF_API int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* peer_flags_dev, void* multicast_ptr,
+                                   int rank, int world, int64_t offset_elems, int64_t n_elems, int num_ctas,
+                                   int num_threads /* 0 = defaults */, void* stream);
+IIF_API size_t iif_allreduce_flag_bytes(void);
 
 #ifdef __cplusplus
 }
