@@ -110,18 +110,22 @@ __device__ __forceinline__ bool grid_tail(double part, int c1, int c5, float* lo
 // TPR threads share one row (NE elements each); a CTA of max(TPR,256) threads holds 256/TPR rows.
 // Small batches use wide rows (TPR = C/4: one 128-bit load per thread, short dependency chains, every
 // SM busy); large batches use NE = 8 for more bytes in flight per SM.
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
 template <int THREADS>
 struct RowSmem {
-  float f[3][THREADS / 32];
+  float f[4][THREADS / 32];
   int i[THREADS / 32];
 };
 
 // The rows `row_block * (THREADS/TPR) ..` of one CTA.  Results for the row of this thread's group come
 // back in (my_loss, cnt, active); only the t == 0 thread of a row group needs them.
-template <int TPR, int NE, bool VEC, int MODE>
+// `hook()` runs (every thread) once the row's loads have returned -- the loss-fused GEMM launch uses it to
+// start its operand TMA stream without queueing the row's own loads behind it.
+template <int TPR, int NE, bool VEC, int MODE, class Hook = NoHook>
 __device__ __forceinline__ void softmax_row_body(const RowArgs& a, int64_t row_block,
                                                  RowSmem<(TPR > 256 ? TPR : 256)>& sm, float& my_loss_out, int& cnt_out,
-                                                 bool& active_out) {
+                                                 bool& active_out, Hook hook = Hook()) {
   constexpr int THREADS = TPR > 256 ? TPR : 256;
   constexpr int WPR = TPR / 32;            // warps per row
   auto& s_f = sm.f;
@@ -141,8 +145,8 @@ __device__ __forceinline__ void softmax_row_body(const RowArgs& a, int64_t row_b
   const bool y_in = active && y >= 0 && y < C;
   const bool y_ok = y_in && y != a.ignore_index;
   const int yi = y_in ? (int)y : -1;
-  // label-dependent scalars: issued now, consumed after the reductions
-  const float sy = (y_in && a.iif) ? __ldg(a.iif + y) : 1.f;
+  // label-dependent scalars: issued now, consumed after the reductions.  (The label's IIF weight is NOT
+  // fetched with a dependent load: the thread that owns the label's column already has it -- see `ay`.)
   float g = 0.f;
   if (MODE == 0 && y_ok) {
     g = a.scale;
@@ -174,6 +178,7 @@ __device__ __forceinline__ void softmax_row_body(const RowArgs& a, int64_t row_b
 
   // ---- pass 1: row max of the scaled logits, arg max, the label's raw logit
   float m = -CUDART_INF_F, bv = -CUDART_INF_F, zy = -CUDART_INF_F;
+  float ay = 0.f;                          // adjusted logit of the label: summed over the row (all other terms +0)
   int bi = 0x7fffffff;
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
@@ -186,12 +191,13 @@ __device__ __forceinline__ void softmax_row_body(const RowArgs& a, int64_t row_b
       const float cmp = a.on_scaled ? sc : z;
       if (in && cmp > bv) { bv = cmp; bi = col; }
     }
-    if (in && col == yi) zy = z;
+    if (in && col == yi) { zy = z; ay = sc; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     zy = fmaxf(zy, __shfl_xor_sync(0xffffffffu, zy, o));
+    ay += __shfl_xor_sync(0xffffffffu, ay, o);
     if (want_arg) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -199,19 +205,22 @@ __device__ __forceinline__ void softmax_row_body(const RowArgs& a, int64_t row_b
     }
   }
   if constexpr (WPR > 1) {
-    if (lane == 0) { s_f[0][warp] = m; s_f[1][warp] = zy; s_f[2][warp] = bv; s_i[warp] = bi; }
+    if (lane == 0) { s_f[0][warp] = m; s_f[1][warp] = zy; s_f[2][warp] = bv; s_f[3][warp] = ay; s_i[warp] = bi; }
     __syncthreads();
-    m = s_f[0][w0]; zy = s_f[1][w0]; bv = s_f[2][w0]; bi = s_i[w0];
+    hook();
+    m = s_f[0][w0]; zy = s_f[1][w0]; bv = s_f[2][w0]; ay = s_f[3][w0]; bi = s_i[w0];
 #pragma unroll
     for (int w = 1; w < WPR; ++w) {
       m = fmaxf(m, s_f[0][w0 + w]);
       zy = fmaxf(zy, s_f[1][w0 + w]);
+      ay += s_f[3][w0 + w];
       const float ov = s_f[2][w0 + w]; const int oi = s_i[w0 + w];
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
     __syncthreads();
   }
-  if (yi < 0) zy = 0.f;
+  if constexpr (WPR == 1) hook();
+  if (yi < 0) { zy = 0.f; ay = 0.f; }
 
   if (MODE == 1 && !a.softmax) {
     // out = z * iif  (cls/custom.py:38)
@@ -235,7 +244,7 @@ __device__ __forceinline__ void softmax_row_body(const RowArgs& a, int64_t row_b
 
   // ---- pass 2: exp-sum; rank of the label (needs the label's logit, now known)
   const float mm = (m == -CUDART_INF_F) ? 0.f : m;
-  const float ref = a.on_scaled ? zy * sy : zy;
+  const float ref = a.on_scaled ? ay : zy;
   float sum = 0.f;
   int cnt = 0;
   const bool need_exp = !(MODE == 1 && !a.softmax);
@@ -287,7 +296,7 @@ __device__ __forceinline__ void softmax_row_body(const RowArgs& a, int64_t row_b
       }
     } else {
       const float lse = mm + logf(sum);
-      my_loss = y_ok ? g * (lse - zy * sy) : 0.f;
+      my_loss = y_ok ? g * (lse - ay) : 0.f;
       if (active && t == 0) {
         if (a.loss_i) a.loss_i[row] = my_loss;
         if (a.lse) a.lse[row] = lse;

@@ -50,6 +50,30 @@ k = dict(hs.kernels())
 hs.launch(); torch.cuda.synchronize()
 if "loss_linear_bwd_bf16" in k:
     show("loss+bwd fused", k["loss_linear_bwd_bf16"])
+# ---- the whole step in place: forward, then the loss-fused backward, back to back after an L2 flush
+def show_step():
+    fns = hs.kernels()
+    bufs = [torch.zeros(4096 * 16, dtype=torch.int64, device=dev) for _ in fns]
+    for _ in range(3):
+        hs.launch()
+    torch.cuda.synchronize()
+    big = torch.empty(512 << 20, dtype=torch.uint8, device=dev); big.zero_(); torch.cuda.synchronize()
+    for (name, fn), b in zip(fns, bufs):
+        lib.iif_debug_timing(b.data_ptr())
+        fn()
+    lib.iif_debug_timing(None)
+    torch.cuda.synchronize()
+    ts = [b.cpu().numpy().reshape(-1, 16) for b in bufs]
+    ts = [t[t[:, 0] > 0] for t in ts]
+    t0 = ts[0][:, 0].min()
+    print(f"== whole step, in place (times relative to the first CTA of the forward launch)")
+    for (name, _), t in zip(fns, ts):
+        print(f"  -- {name}: {len(t)} CTAs")
+        for i, n in enumerate(NAMES):
+            col = t[:, i]; col = col[col > 0]
+            if len(col):
+                print(f"     {n:14s} median {np.median(col - t0) / 1e3:7.2f}  min {(col.min() - t0) / 1e3:7.2f}  max {(col.max() - t0) / 1e3:7.2f} us")
+show_step()
 for i in range(3):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(); ops.linear_fwd(x, w, bias); t1.record(); torch.cuda.synchronize()
