@@ -263,6 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     };
     for (int64_t r = blockIdx.x; r < g.loss.B; r += gridDim.x) {
       float my_loss; int cnt; bool active;
+      if (r + gridDim.x < g.loss.B) prefetch_row_block<256, (FUSE_NE ? FUSE_NE : 4), true>(g.loss, r + gridDim.x);
       softmax_row_body<256, (FUSE_NE ? FUSE_NE : 4), true, 0>(g.loss, r, row_sm, my_loss, cnt, active, issue_b);
       if (threadIdx.x == 0) { loss_part += (double)my_loss; loss_c1 += cnt < 1; loss_c5 += cnt < 5; }
       __syncthreads();

@@ -12,7 +12,7 @@ namespace iif {
 
 // MODE 0: softmax-CE forward + backward.  MODE 1: activation (softmax(z*iif) or z*iif).
 template <int TPR, int NE, bool VEC, int MODE>
-__global__ void __launch_bounds__(TPR > 256 ? TPR : 256)
+__global__ void __launch_bounds__(TPR > 256 ? TPR : 256, TPR > 256 ? 1 : (NE <= 8 ? 4 : 3))
 row_softmax_kernel(const RowArgs a) {
   constexpr int THREADS = TPR > 256 ? TPR : 256;
   __shared__ RowSmem<THREADS> sm;
@@ -20,25 +20,36 @@ row_softmax_kernel(const RowArgs a) {
   __shared__ int s_row_rank[THREADS / TPR];
   ptx::griddep_launch_dependents();   // the successor's prologue may start; its own wait still orders it after us
   ptx::griddep_wait();
-  float my_loss; int cnt; bool active;
-  softmax_row_body<TPR, NE, VEC, MODE>(a, blockIdx.x, sm, my_loss, cnt, active);
-  if constexpr (MODE == 0) {
-    if (a.loss_sum || a.acc_counts) {
-      // CTA partial in row order, then the grid tail
-      const int t = threadIdx.x % TPR, lrow = threadIdx.x / TPR;
-      if (t == 0) { s_row_loss[lrow] = active ? my_loss : 0.f; s_row_rank[lrow] = active ? cnt : 0x7fffffff; }
-      __syncthreads();
-      double part = 0.0;
-      int c1 = 0, c5 = 0;
-      if (threadIdx.x == 0) {
+  // Row blocks are walked by a bounded grid (launch_row): with one CTA per row block a 64k-row batch sent
+  // 32k CTAs through the ticket of the deterministic tail -- same-address atomics serialise in L2 at ~9 ns
+  // each, which was the whole kernel time (293 us for 65536 x 1000, 21 % of HBM bandwidth).
+  constexpr int RPB = THREADS / TPR;
+  const int64_t nblocks = (a.B + RPB - 1) / RPB;
+  double part = 0.0;
+  int c1 = 0, c5 = 0;
+  for (int64_t rb = blockIdx.x; rb < nblocks; rb += gridDim.x) {
+    float my_loss; int cnt; bool active;
+    if (rb + gridDim.x < nblocks) prefetch_row_block<TPR, NE, VEC>(a, rb + gridDim.x);
+    softmax_row_body<TPR, NE, VEC, MODE>(a, rb, sm, my_loss, cnt, active);
+    if constexpr (MODE == 0) {
+      if (a.loss_sum || a.acc_counts) {
+        // CTA partial in row order
+        const int t = threadIdx.x % TPR, lrow = threadIdx.x / TPR;
+        if (t == 0) { s_row_loss[lrow] = active ? my_loss : 0.f; s_row_rank[lrow] = active ? cnt : 0x7fffffff; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int r = 0; r < THREADS / TPR; ++r) {
-          part += (double)s_row_loss[r];
-          c1 += s_row_rank[r] < 1; c5 += s_row_rank[r] < 5;
+          for (int r = 0; r < RPB; ++r) {
+            part += (double)s_row_loss[r];
+            c1 += s_row_rank[r] < 1; c5 += s_row_rank[r] < 5;
+          }
         }
       }
-      grid_tail<THREADS>(part, c1, c5, a.loss_sum, a.acc_counts, a.scratch);
     }
+    __syncthreads();                      // the reduction scratch is reused by the next row block
+  }
+  if constexpr (MODE == 0) {
+    if (a.loss_sum || a.acc_counts) grid_tail<THREADS>(part, c1, c5, a.loss_sum, a.acc_counts, a.scratch);
   }
 }
 
@@ -47,7 +58,9 @@ static int launch_row(const RowArgs& a, bool vec, cudaStream_t st) {
   constexpr int THREADS = TPR > 256 ? TPR : 256;
   constexpr int RPB = THREADS / TPR;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)((a.B + RPB - 1) / RPB));
+  const int64_t nblocks = (a.B + RPB - 1) / RPB;
+  const int64_t cap = (int64_t)kNumSMs * (THREADS >= 1024 ? 2 : (THREADS >= 512 ? 4 : 8));   // one resident wave
+  cfg.gridDim = dim3((unsigned)(nblocks < cap ? nblocks : cap));
   cfg.blockDim = dim3(THREADS);
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -63,14 +76,20 @@ static int launch_row(const RowArgs& a, bool vec, cudaStream_t st) {
 
 // rows per CTA of the configuration dispatch_row would pick (for the scratch size)
 static int row_config(int64_t B, int C, int* tpr, int* ne) {
-  const bool big = B > 2048;                 // plenty of rows: favour bytes in flight over row width
+  // Small batches (latency): wide rows, one 128-bit load per thread, every SM busy.
+  // Big batches (throughput): FEW threads per row, 16-32 logits each -- the per-row fixed cost (two
+  // reductions, label bookkeeping, pointer arithmetic: ~250 instructions per thread) is what made the
+  // 8-logits-per-thread configuration issue-bound at 35 % of HBM bandwidth; one warp per row also drops both
+  // block barriers.
+  const bool big = B > 2048;
   if (C <= 128) { *tpr = 32; *ne = 4; }
   else if (C <= 256) { if (big) { *tpr = 32; *ne = 8; } else { *tpr = 64; *ne = 4; } }
-  else if (C <= 512) { if (big) { *tpr = 64; *ne = 8; } else { *tpr = 128; *ne = 4; } }
-  else if (C <= 1024) { if (big) { *tpr = 128; *ne = 8; } else { *tpr = 256; *ne = 4; } }
-  else if (C <= 2048) { *tpr = 256; *ne = 8; }
-  else if (C <= 4096) { *tpr = 256; *ne = 16; }
+  else if (C <= 512) { if (big) { *tpr = 32; *ne = 16; } else { *tpr = 128; *ne = 4; } }
+  else if (C <= 1024) { if (big) { *tpr = 32; *ne = 32; } else { *tpr = 256; *ne = 4; } }
+  else if (C <= 2048) { if (big) { *tpr = 64; *ne = 32; } else { *tpr = 256; *ne = 8; } }
+  else if (C <= 4096) { if (big) { *tpr = 128; *ne = 32; } else { *tpr = 256; *ne = 16; } }
   else if (C <= 8192) { *tpr = 256; *ne = 32; }
+  else if (C <= 10240) { *tpr = 256; *ne = 40; }        // the 10000-class sweep: one block per row, no padding waste
   else if (C <= 16384) { *tpr = 512; *ne = 32; }
   else if (C <= 32768) { *tpr = 1024; *ne = 32; }
   else return IIF_EUNSUPPORTED;
@@ -84,6 +103,7 @@ static int dispatch_row(const RowArgs& a, bool vec, cudaStream_t st) {
 #define IIF_ROW(T, N) if (tpr == T && ne == N) return launch_row<T, N, MODE>(a, vec, st)
   IIF_ROW(32, 4); IIF_ROW(32, 8); IIF_ROW(64, 4); IIF_ROW(64, 8); IIF_ROW(128, 4); IIF_ROW(128, 8);
   IIF_ROW(256, 4); IIF_ROW(256, 8); IIF_ROW(256, 16); IIF_ROW(256, 32); IIF_ROW(512, 32); IIF_ROW(1024, 32);
+  IIF_ROW(32, 16); IIF_ROW(32, 32); IIF_ROW(64, 32); IIF_ROW(128, 32); IIF_ROW(256, 40);
 #undef IIF_ROW
   return IIF_EUNSUPPORTED;
 }
@@ -116,9 +136,12 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
   ptx::griddep_launch_dependents();   // the successor's prologue may start; its own wait still orders it after us
   ptx::griddep_wait();
   const int t = threadIdx.x % TPR;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x / TPR) + threadIdx.x / TPR;
-  const bool active = row < a.B;
   const int C = a.C;
+  double part = 0.0;                         // thread 0: this CTA's loss, row pairs in order
+  // bounded grid walking the row pairs (see row_softmax_kernel: the tail's ticket must not see 32k CTAs)
+  for (int64_t rp = blockIdx.x; rp * 2 < a.B; rp += gridDim.x) {
+  const int64_t row = rp * 2 + threadIdx.x / TPR;
+  const bool active = row < a.B;
   float acc = 0.f;
   if (active) {
     const int64_t y = a.label[row];
@@ -165,15 +188,13 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
   const int w0 = (warp / 4) * 4;
   acc = (s_sum[w0] + s_sum[w0 + 1]) + (s_sum[w0 + 2] + s_sum[w0 + 3]);
   if (active && t == 0 && a.loss_i) a.loss_i[row] = acc;
-  if (a.loss_sum) {
-    double part = 0.0;
-    if (threadIdx.x == 0) {
-      part = (double)((s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]));
-      const int64_t row1 = (int64_t)blockIdx.x * 2 + 1;
-      if (row1 < a.B) part += (double)((s_sum[4] + s_sum[5]) + (s_sum[6] + s_sum[7]));
-    }
-    grid_tail<256>(part, 0, 0, a.loss_sum, nullptr, a.scratch);
+  if (a.loss_sum && threadIdx.x == 0) {
+    part += (double)((s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]));
+    if (rp * 2 + 1 < a.B) part += (double)((s_sum[4] + s_sum[5]) + (s_sum[6] + s_sum[7]));
   }
+  __syncthreads();                           // s_sum is reused by the next row pair
+  }
+  if (a.loss_sum) grid_tail<256>(part, 0, 0, a.loss_sum, nullptr, a.scratch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -286,7 +307,8 @@ extern "C" int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_
                    (!col_weight || aligned16(col_weight)) && (!loss_elem || (aligned16(loss_elem) && ldl % 4 == 0)) &&
                    (!dz_f32 || (aligned16(dz_f32) && lddz_f32 % 4 == 0)) &&
                    (!dz_bf16 || ((reinterpret_cast<uintptr_t>(dz_bf16) & 7u) == 0 && lddz_bf16 % 4 == 0));
-  const unsigned grid = (unsigned)((B + 1) / 2);
+  const int64_t pairs = (B + 1) / 2;
+  const unsigned grid = (unsigned)(pairs < 8 * kNumSMs ? pairs : 8 * kNumSMs);
   if (vec) bce_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   else bce_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return launch_status();
