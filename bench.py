@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--sync-allreduce", action="store_true", help="N>1: all-reduce on the compute stream (no overlap)")
     ap.add_argument("--ar-ctas", type=int, default=0)
     ap.add_argument("--ar-threads", type=int, default=0)
+    ap.add_argument("--ar-lanes", type=int, default=2, help="all-reduces of consecutive steps in flight at once")
     ap.add_argument("--py-loop", action="store_true", help="N>1: drive steps + all-reduce from Python (graph replay) instead of the C pipeline")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "peer-nomc", "nccl"],
                     help="N>1: the library's NVLink peer-memory kernel (with / without NVLS multicast) or NCCL")
@@ -187,8 +188,9 @@ def main():
     if world > 1 and args.allreduce != "nccl":
         from iif_b200.parallel import PeerAllReduce
         peer = PeerAllReduce(C * D + C, S, dev, use_multicast=(args.allreduce == "peer"), num_ctas=args.ar_ctas,
-                             num_threads=args.ar_threads)
+                             num_threads=args.ar_threads, lanes=args.ar_lanes)
         ar_kind = "peer-memory kernel" + (" (NVLS multimem)" if peer.multicast else " (peer loads/stores)")
+        ar_kind += f", {peer.lanes} in flight"
     shared_ws = torch.zeros(max(int(ops._lib.load().iif_gemm_ws_bytes(B, D, C)), 1), dtype=torch.uint8, device=dev)
     for s in range(S):
         x = torch.randn(B, D, generator=g).to(dev).to(torch.bfloat16)

@@ -59,12 +59,12 @@ SIGNATURES = {
     "iif_debug_timing": (None, [_p]),
     "iif_debug_timing_allreduce": (None, [_p]),
     "iif_debug_capacity": (_i32, [_p]),
-    "iif_allreduce_mean_f32": (_i32, [_p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _p]),
+    "iif_allreduce_mean_f32": (_i32, [_p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _i32, _p]),
     "iif_allreduce_flag_bytes": (_sz, []),
     "iif_pipeline_create": (_i32, [C.POINTER(_p), C.POINTER(HeadArgs), _i32]),
     "iif_pipeline_submit": (_i32, [_p, _i32, _p, _p, _p]),
     "iif_pipeline_submit_device": (_i32, [_p, _i32]),
-    "iif_pipeline_set_allreduce": (_i32, [_p, _p, _p, _p, _i32, _i32, C.POINTER(_i64), _i64, _i32, _i32]),
+    "iif_pipeline_set_allreduce": (_i32, [_p, _p, _p, _p, _i32, _i32, C.POINTER(_i64), _i64, _i32, _i32, _i32]),
     "iif_pipeline_get_streams": (_i32, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
     "iif_pipeline_wait": (_i32, [_p, _i32]),
     "iif_pipeline_stream_wait_step": (_i32, [_p, _i32, _p]),

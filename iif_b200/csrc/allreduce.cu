@@ -23,6 +23,8 @@ namespace iif {
 constexpr int AR_MAX_WORLD = 16;
 constexpr int AR_MAX_CTAS = 64;
 constexpr int AR_THREADS = 512;
+constexpr int AR_LANES = 4;             // independent flag sets: up to 4 all-reduces of one rank may be in flight
+constexpr size_t AR_LANE_WORDS = (size_t)AR_MAX_CTAS * AR_MAX_WORLD + AR_MAX_CTAS;
 
 // Cross-rank barrier among the CTAs with the same blockIdx.  Flags only ever grow: launch number e (kept
 // per CTA in the rank's own flag memory) uses the values 2e (phase 0) and 2e+1 (phase 1); a signal is a
@@ -35,9 +37,10 @@ constexpr int AR_THREADS = 512;
 // gradients it announces were written by the PREVIOUS kernel of the stream, and nothing read after either
 // handshake can be stale -- peer data is read with ld.cv / multimem (never from a cached copy), and the
 // reduced result is consumed by later kernels out of this GPU's own L2.
-__device__ __forceinline__ void ar_barrier(uint32_t* const* flags, int rank, int world, uint32_t value, bool release) {
+__device__ __forceinline__ void ar_barrier(uint32_t* const* flags, size_t lane_off, int rank, int world, uint32_t value,
+                                           bool release) {
   __syncthreads();
-  const size_t slot = (size_t)blockIdx.x * AR_MAX_WORLD;
+  const size_t slot = lane_off + (size_t)blockIdx.x * AR_MAX_WORLD;
   if (threadIdx.x == 0) {
     if (release) asm volatile("fence.acq_rel.sys;" ::: "memory");
     for (int p = 0; p < world; ++p)
@@ -90,12 +93,13 @@ __device__ __forceinline__ void ar_stamp(long long* dbg, int slot) {
 template <bool MULTICAST, int U>
 __global__ void __launch_bounds__(AR_THREADS, 1)
 allreduce_mean_kernel(float* const* bufs, uint32_t* const* flags, float* mc, int rank, int world, int64_t n4,
-                      int64_t off4, long long* dbg) {
+                      int64_t off4, int lane, long long* dbg) {
   ar_stamp(dbg, 0);
+  const size_t lane_off = (size_t)lane * AR_LANE_WORDS;
   // launch number of this CTA (stream-ordered launches: no race), stored next to the flags
-  uint32_t* epoch_p = flags[rank] + (size_t)AR_MAX_CTAS * AR_MAX_WORLD + blockIdx.x;
+  uint32_t* epoch_p = flags[rank] + lane_off + (size_t)AR_MAX_CTAS * AR_MAX_WORLD + blockIdx.x;
   const uint32_t epoch = *epoch_p + 1;
-  ar_barrier(flags, rank, world, 2 * epoch, false);
+  ar_barrier(flags, lane_off, rank, world, 2 * epoch, false);
   if (threadIdx.x == 0) *epoch_p = epoch;
   ar_stamp(dbg, 1);
   const int64_t per = (n4 + world - 1) / world;                    // float4 per rank slice
@@ -149,7 +153,7 @@ allreduce_mean_kernel(float* const* bufs, uint32_t* const* flags, float* mc, int
     }
   }
   ar_stamp(dbg, 2);
-  ar_barrier(flags, rank, world, 2 * epoch + 1, true);            // release: our peer stores land before the "done" flag
+  ar_barrier(flags, lane_off, rank, world, 2 * epoch + 1, true);            // release: our peer stores land before the "done" flag
   ar_stamp(dbg, 3);
 }
 
@@ -161,13 +165,14 @@ static long long* g_ar_dbg = nullptr;
 extern "C" void iif_debug_timing_allreduce(long long* buf) { g_ar_dbg = buf; }
 
 extern "C" size_t iif_allreduce_flag_bytes(void) {
-  return ((size_t)AR_MAX_CTAS * AR_MAX_WORLD + AR_MAX_CTAS) * sizeof(uint32_t);   // [cta][peer] flags + [cta] launch numbers
+  return AR_LANES * AR_LANE_WORDS * sizeof(uint32_t);   // per lane: [cta][peer] flags + [cta] launch numbers
 }
 
 extern "C" int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* peer_flags_dev, void* multicast_ptr, int rank,
                                       int world, int64_t offset_elems, int64_t n_elems, int num_ctas, int num_threads,
-                                      void* stream) {
+                                      int lane, void* stream) {
   if (!peer_bufs_dev || !peer_flags_dev || world < 1 || world > AR_MAX_WORLD || rank < 0 || rank >= world) return IIF_EINVAL;
+  if (lane < 0 || lane >= AR_LANES) return IIF_EINVAL;
   if (n_elems < 0 || offset_elems < 0 || (n_elems & 3) || (offset_elems & 3)) return IIF_EALIGN;
   if (n_elems == 0) return IIF_OK;
   if (num_ctas <= 0) num_ctas = 16;
@@ -179,9 +184,9 @@ extern "C" int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* p
   cudaStream_t st = (cudaStream_t)stream;
   float* mc = reinterpret_cast<float*>(multicast_ptr);
   const int64_t n4 = n_elems / 4, off4 = offset_elems / 4;
-  if (mc) allreduce_mean_kernel<true, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, g_ar_dbg);
-  else if (world <= 2) allreduce_mean_kernel<false, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, g_ar_dbg);
-  else if (world <= 4) allreduce_mean_kernel<false, 4><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, g_ar_dbg);
-  else allreduce_mean_kernel<false, 2><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, g_ar_dbg);
+  if (mc) allreduce_mean_kernel<true, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg);
+  else if (world <= 2) allreduce_mean_kernel<false, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg);
+  else if (world <= 4) allreduce_mean_kernel<false, 4><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg);
+  else allreduce_mean_kernel<false, 2><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg);
   return launch_status();
 }

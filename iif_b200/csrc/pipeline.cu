@@ -18,7 +18,8 @@ struct iif_pipeline {
     int64_t ar_offset;
   };
   int nslots;
-  cudaStream_t s_h2d, s_compute, s_d2h, s_comm;
+  cudaStream_t s_h2d, s_compute, s_d2h, s_comm[4];
+  int ar_lanes, ar_next;
   Slot* slots;
   // optional data-parallel exchange after every step (iif_pipeline_set_allreduce)
   bool ar_on;
@@ -48,8 +49,9 @@ extern "C" int iif_pipeline_create(iif_pipeline** out, const iif_head_args* slot
   {  // the all-reduce gates the reuse of gradient buffers: let its CTAs be scheduled ahead of queued GEMM CTAs
     int lo = 0, hi = 0;
     IIF_CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    IIF_CU(cudaStreamCreateWithPriority(&p->s_comm, cudaStreamNonBlocking, hi));
+    for (int l = 0; l < 4; ++l) IIF_CU(cudaStreamCreateWithPriority(&p->s_comm[l], cudaStreamNonBlocking, hi));
   }
+  p->ar_lanes = 1;
   for (int i = 0; i < nslots; ++i) {
     iif_pipeline::Slot& s = p->slots[i];
     s.a = slot_args[i];
@@ -64,11 +66,13 @@ extern "C" int iif_pipeline_create(iif_pipeline** out, const iif_head_args* slot
 
 extern "C" int iif_pipeline_set_allreduce(iif_pipeline* p, void* const* peer_bufs_dev, void* const* peer_flags_dev,
                                           void* multicast_ptr, int rank, int world, const int64_t* slot_offsets_elems,
-                                          int64_t n_elems, int num_ctas, int num_threads) {
+                                          int64_t n_elems, int num_ctas, int num_threads, int num_lanes) {
+  if (num_lanes < 1 || num_lanes > 4) return IIF_EINVAL;
   if (!p || !peer_bufs_dev || !peer_flags_dev || !slot_offsets_elems || world < 1 || rank < 0 || rank >= world) return IIF_EINVAL;
   p->ar_bufs = peer_bufs_dev; p->ar_flags = peer_flags_dev; p->ar_mc = multicast_ptr;
   p->ar_rank = rank; p->ar_world = world; p->ar_n = n_elems; p->ar_ctas = num_ctas; p->ar_threads = num_threads;
   for (int i = 0; i < p->nslots; ++i) p->slots[i].ar_offset = slot_offsets_elems[i];
+  p->ar_lanes = num_lanes; p->ar_next = 0;
   p->ar_on = world > 1;
   return IIF_OK;
 }
@@ -79,11 +83,13 @@ static int run_step(iif_pipeline* p, iif_pipeline::Slot& s) {
   if (int rc = iif_head_fwd_bwd_bf16(&s.a, p->s_compute)) return rc;
   IIF_CU(cudaEventRecord(s.step_done, p->s_compute));
   if (p->ar_on) {
-    IIF_CU(cudaStreamWaitEvent(p->s_comm, s.step_done, 0));
+    const int lane = p->ar_next;
+    p->ar_next = (p->ar_next + 1) % p->ar_lanes;
+    IIF_CU(cudaStreamWaitEvent(p->s_comm[lane], s.step_done, 0));
     if (int rc = iif_allreduce_mean_f32(p->ar_bufs, p->ar_flags, p->ar_mc, p->ar_rank, p->ar_world, s.ar_offset, p->ar_n,
-                                        p->ar_ctas, p->ar_threads, p->s_comm))
+                                        p->ar_ctas, p->ar_threads, lane, p->s_comm[lane]))
       return rc;
-    IIF_CU(cudaEventRecord(s.release, p->s_comm));
+    IIF_CU(cudaEventRecord(s.release, p->s_comm[lane]));
     s.held = true;
   }
   return IIF_OK;
@@ -123,7 +129,7 @@ extern "C" int iif_pipeline_get_streams(iif_pipeline* p, void** h2d, void** comp
   if (h2d) *h2d = p->s_h2d;
   if (compute) *compute = p->s_compute;
   if (d2h) *d2h = p->s_d2h;
-  if (comm) *comm = p->s_comm;
+  if (comm) *comm = p->s_comm[0];
   return IIF_OK;
 }
 
@@ -152,7 +158,7 @@ extern "C" int iif_pipeline_sync(iif_pipeline* p) {
   IIF_CU(cudaStreamSynchronize(p->s_h2d));
   IIF_CU(cudaStreamSynchronize(p->s_compute));
   IIF_CU(cudaStreamSynchronize(p->s_d2h));
-  IIF_CU(cudaStreamSynchronize(p->s_comm));
+  for (int l = 0; l < 4; ++l) IIF_CU(cudaStreamSynchronize(p->s_comm[l]));
   return IIF_OK;
 }
 
@@ -168,7 +174,7 @@ extern "C" void iif_pipeline_destroy(iif_pipeline* p) {
   cudaStreamDestroy(p->s_h2d);
   cudaStreamDestroy(p->s_compute);
   cudaStreamDestroy(p->s_d2h);
-  cudaStreamDestroy(p->s_comm);
+  for (int l = 0; l < 4; ++l) cudaStreamDestroy(p->s_comm[l]);
   delete[] p->slots;
   delete p;
 }

@@ -528,7 +528,8 @@ class HeadPipeline:
         offs = (C.c_int64 * n)(*[i * peer.stride for i in range(n)])
         self._peer = peer
         _lib.check(self._lib.iif_pipeline_set_allreduce(self._h, peer._bufs, peer._flags, peer._mc, peer.rank, peer.world,
-                                                        offs, (peer.numel + 3) // 4 * 4, peer.num_ctas, peer.num_threads),
+                                                        offs, (peer.numel + 3) // 4 * 4, peer.num_ctas, peer.num_threads,
+                                                        peer.lanes),
                    "pipeline_set_allreduce")
 
     def streams(self):

@@ -88,7 +88,7 @@ class PeerAllReduce:
     without a group): callers fall back to `allreduce_mean_` explicitly -- never silently."""
 
     def __init__(self, numel: int, nbuf: int, device, group=None, use_multicast: bool = True, num_ctas: int = 0,
-                 num_threads: int = 0):
+                 num_threads: int = 0, lanes: int = 2):
         from . import _lib
         import torch.distributed._symmetric_memory as symm_mem
         if not dist.is_initialized():
@@ -105,7 +105,8 @@ class PeerAllReduce:
         self.num_threads = int(num_threads) if num_threads else 256
         # The all-reduce overlaps the next step's GEMM launches and blocks on other GPUs: keep its footprint
         # out of the resident-CTA budget their in-kernel rendezvous rely on (include/iif_b200.h).
-        self._check(self._lib.iif_gemm_reserve_slots(self.num_ctas * (1 if self.num_threads <= 256 else 2)),
+        self.lanes = max(1, min(int(lanes), 4))     # all-reduces of consecutive steps that may be in flight at once
+        self._check(self._lib.iif_gemm_reserve_slots(self.lanes * self.num_ctas * (1 if self.num_threads <= 256 else 2)),
                     "gemm_reserve_slots")
         try:
             self.mem = symm_mem.empty(self.nbuf * self.stride, dtype=torch.float32, device=self.device)
@@ -128,9 +129,9 @@ class PeerAllReduce:
     def buffer(self, i: int) -> torch.Tensor:
         return self.mem[i * self.stride: i * self.stride + self.numel]
 
-    def all_reduce(self, i: int, stream: torch.cuda.Stream) -> None:
+    def all_reduce(self, i: int, stream: torch.cuda.Stream, lane: int = 0) -> None:
         n = (self.numel + 3) // 4 * 4           # the slot is padded: reduce whole float4s
         rc = self._lib.iif_allreduce_mean_f32(self._bufs, self._flags, self._mc, self.rank, self.world, i * self.stride, n,
-                                              self.num_ctas, self.num_threads, C.c_void_p(stream.cuda_stream))
+                                              self.num_ctas, self.num_threads, lane, C.c_void_p(stream.cuda_stream))
         if rc:
             self._check(rc, "allreduce_mean_f32")

@@ -286,10 +286,12 @@ IIF_API int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x, c
 IIF_API int iif_pipeline_submit_device(iif_pipeline* p, int slot);
 /* Data-parallel runs: after every step, all-reduce(mean) the slot's gradient slice with
  * iif_allreduce_mean_f32 on the pipeline's comm stream (arguments as there; slot i's slice starts at
- * slot_offsets_elems[i]); the slot is not reused before its all-reduce has finished. */
+ * slot_offsets_elems[i]); the slot is not reused before its all-reduce has finished.  num_lanes (1..4)
+ * comm streams take the all-reduces of consecutive steps in turn, so that many can be in flight at once
+ * (an 8 MB all-reduce is a chain of NVLink round trips longer than the step it overlaps). */
 IIF_API int iif_pipeline_set_allreduce(iif_pipeline* p, void* const* peer_bufs_dev, void* const* peer_flags_dev,
                                        void* multicast_ptr, int rank, int world, const int64_t* slot_offsets_elems,
-                                       int64_t n_elems, int num_ctas, int num_threads);
+                                       int64_t n_elems, int num_ctas, int num_threads, int num_lanes);
 /* The pipeline's streams (cudaStream_t), e.g. to record timing events on them; any pointer may be NULL. */
 IIF_API int iif_pipeline_get_streams(iif_pipeline* p, void** h2d, void** compute, void** d2h, void** comm);
 /* Block until the slot's latest step has delivered its loss to host_loss. */
@@ -312,12 +314,14 @@ IIF_API void iif_pipeline_destroy(iif_pipeline* p);
  *                    ZERO when first used (monotonic launch counters; never reset them afterwards)
  *   multicast_ptr  : NVLS multicast mapping of the buffer, or NULL (then plain peer loads / stores)
  *   offset_elems, n_elems : the slice of the buffer to reduce, both multiples of 4
+ *   lane           : all-reduces of one rank that may be IN FLIGHT AT THE SAME TIME (different streams)
+ *                    must use different lanes (separate flag sets); calls on one lane must be stream-ordered
  * Collective: every rank must launch it with the same arguments (its own rank aside), stream-ordered
  * after the rank's own writes to the slice.  In place; the result is bit-identical on every rank.
  * ------------------------------------------------------------------------------------------- */
 IIF_API int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* peer_flags_dev, void* multicast_ptr,
                                    int rank, int world, int64_t offset_elems, int64_t n_elems, int num_ctas,
-                                   int num_threads /* 0 = defaults */, void* stream);
+                                   int num_threads /* 0 = defaults */, int lane /* 0..3 */, void* stream);
 IIF_API size_t iif_allreduce_flag_bytes(void);
 
 #ifdef __cplusplus

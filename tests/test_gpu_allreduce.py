@@ -26,11 +26,11 @@ def test_allreduce_world1_identity():
     fl = torch.tensor([flags.data_ptr()], dtype=torch.int64, device=dev)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     for _ in range(3):   # flags / launch numbers advance monotonically
-        _lib.check(lib.iif_allreduce_mean_f32(C.c_void_p(bufs.data_ptr()), C.c_void_p(fl.data_ptr()), None, 0, 1, 0, n4, 0, 0, st))
+        _lib.check(lib.iif_allreduce_mean_f32(C.c_void_p(bufs.data_ptr()), C.c_void_p(fl.data_ptr()), None, 0, 1, 0, n4, 0, 0, _ % 2, st))
     torch.cuda.synchronize()
     assert torch.equal(buf, ref)
-    assert lib.iif_allreduce_mean_f32(C.c_void_p(bufs.data_ptr()), C.c_void_p(fl.data_ptr()), None, 0, 1, 0, 6, 0, 0, st) == _lib.EALIGN
-    assert lib.iif_allreduce_mean_f32(C.c_void_p(bufs.data_ptr()), C.c_void_p(fl.data_ptr()), None, 2, 1, 0, 8, 0, 0, st) == _lib.EINVAL
+    assert lib.iif_allreduce_mean_f32(C.c_void_p(bufs.data_ptr()), C.c_void_p(fl.data_ptr()), None, 0, 1, 0, 6, 0, 0, 0, st) == _lib.EALIGN
+    assert lib.iif_allreduce_mean_f32(C.c_void_p(bufs.data_ptr()), C.c_void_p(fl.data_ptr()), None, 2, 1, 0, 8, 0, 0, 0, st) == _lib.EINVAL
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs with NVLink peer access")
