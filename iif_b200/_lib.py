@@ -43,6 +43,8 @@ SIGNATURES = {
     "iif_softmax_ce_fwd_bwd": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _f32, _i64, _i64, _p, _p, _p, _i64, _p, _i64,
                                       _p, _p, _p, _p, _p, _p]),
     "iif_loss_scratch_bytes": (_sz, [_i64]),
+    "iif_softmax_ce_mixup_fwd_bwd": (_i32, [_p, _i64, _p, _p, _p, _f32, _p, _p, _i64, _f32, _i64, _i64, _p, _p, _p, _i64,
+                                            _p, _i64, _p, _p, _p, _p, _p]),
     "iif_scaled_activation": (_i32, [_p, _i64, _p, _i32, _i64, _i64, _p, _i64, _p, _p, _p, _p]),
     "iif_sigmoid_bce_fwd_bwd": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _f32, _i64, _i64, _p, _i64, _p, _p, _p, _i64,
                                        _p, _i64, _p, _p]),

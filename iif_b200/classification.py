@@ -44,6 +44,18 @@ class IIFLoss(nn.Module):
             return F_.iif_cross_entropy(pred, s, targets, class_weight=self.weight, scale=1.0)
         return F_.iif_cross_entropy(pred, s, targets, class_weight=self.weight, scale=1.0, reduce=False)
 
+    def mixup_forward(self, pred, y_a, y_b, lam):
+        """lam * self(pred, y_a) + (1 - lam) * self(pred, y_b)  (custom.py:116-117) from ONE pass over the logits.
+        Raises ops.Unsupported when the fused kernel does not cover the shape (C % 4 != 0)."""
+        s = self.iif[self.variant]
+        B = pred.shape[0]
+        kw = dict(class_weight=self.weight, target_b=y_b, lam=float(lam))
+        if self.reduction == "mean":
+            return F_.iif_cross_entropy(pred, s, y_a, scale=1.0 / max(B, 1), **kw)
+        if self.reduction == "sum":
+            return F_.iif_cross_entropy(pred, s, y_a, scale=1.0, **kw)
+        return F_.iif_cross_entropy(pred, s, y_a, scale=1.0, reduce=False, **kw)
+
 
 class FocalLoss(nn.Module):
     """classification/custom.py:42-89, gamma == 0 branch (= sigmoid BCE, `--classif bce`).
@@ -70,7 +82,9 @@ class FocalLoss(nn.Module):
 
 
 class Mixup(object):
-    """classification/custom.py:91-117 (unchanged semantics; the criterion is called twice)."""
+    """classification/custom.py:91-117.  `mixup_criterion` evaluates both terms in ONE fused pass when the
+    criterion offers `mixup_forward` (iif_b200 IIFLoss) and the shape qualifies; otherwise the criterion is
+    called twice exactly as in the reference."""
 
     def __init__(self, criterion, alpha=1):
         self.alpha = alpha
@@ -84,6 +98,12 @@ class Mixup(object):
         return mixed_x, y, y[index], lam
 
     def mixup_criterion(self, pred, y_a, y_b, lam):
+        fused = getattr(self.criterion, "mixup_forward", None)
+        if fused is not None:
+            try:
+                return fused(pred, y_a, y_b, lam)
+            except ops.Unsupported:
+                pass
         return lam * self.criterion(pred, y_a) + (1 - lam) * self.criterion(pred, y_b)
 
 

@@ -342,3 +342,26 @@ extern "C" int iif_colsum(const void* dz, int dz_dtype, int64_t lddz, const floa
   else colsum_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dz, lddz, alpha_dev, rows, (int)cols, db);
   return launch_status();
 }
+
+// Mixup: lam * CE(label_a) + (1 - lam) * CE(label_b) and its gradient from ONE pass over the logits
+// (cls/custom.py:116-117 calls the criterion twice on the same logits).  128-bit path only:
+// IIF_EUNSUPPORTED when C % 4 != 0 or the rows are unaligned (the caller then runs two passes).
+extern "C" int iif_softmax_ce_mixup_fwd_bwd(const float* z, int64_t ldz, const float* iifv, const int64_t* label_a,
+                                            const int64_t* label_b, float lam, const float* class_weight,
+                                            const float* sample_weight, int64_t ignore_index, float scale, int64_t B,
+                                            int64_t C, float* loss_i, float* loss_sum, float* dz_f32, int64_t lddz_f32,
+                                            void* dz_bf16, int64_t lddz_bf16, int32_t* argmax, int32_t* rank,
+                                            int32_t* acc_counts, int32_t* scratch, void* stream) {
+  if (B < 0 || C <= 0 || (B > 0 && (!z || !label_a || !label_b)) || ldz < C) return IIF_EINVAL;
+  if ((dz_f32 && lddz_f32 < C) || (dz_bf16 && lddz_bf16 < C)) return IIF_EINVAL;
+  if ((acc_counts && !rank) || ((loss_sum || acc_counts) && !scratch)) return IIF_EINVAL;
+  if (C > 32768) return IIF_EUNSUPPORTED;
+  if (B == 0) return IIF_OK;
+  RowArgs a{};
+  const bool vec = make_ce_row_args(a, z, ldz, iifv, label_a, class_weight, sample_weight, ignore_index, scale, B, C, loss_i,
+                                    loss_sum, dz_f32, lddz_f32, dz_bf16, lddz_bf16, nullptr, argmax, rank, acc_counts, scratch);
+  if (!vec) return IIF_EUNSUPPORTED;
+  a.label_b = label_b;
+  a.lam = lam;
+  return dispatch_row<0>(a, true, (cudaStream_t)stream);
+}

@@ -23,6 +23,8 @@ struct RowArgs {
   uint16_t* dz16; int64_t lddz16;
   float* lse; int32_t* argmax; int32_t* rank; int32_t* acc_counts; int32_t* scratch;
   float* out; int64_t ldo; int softmax; int on_scaled;
+  // dual-label (Mixup) loss: lam * CE(label) + (1 - lam) * CE(label_b) from ONE softmax pass (128-bit path only)
+  const int64_t* label_b; float lam;
 };
 
 // Fill the arguments of the softmax-CE rows; returns whether the 128-bit (VEC) path is legal.
@@ -114,7 +116,7 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 
 template <int THREADS>
 struct RowSmem {
-  float f[4][THREADS / 32];
+  float f[5][THREADS / 32];
   int i[THREADS / 32];
 };
 
@@ -163,6 +165,21 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
     if (a.cw) g *= __ldg(a.cw + y);
     if (a.sw) g *= __ldg(a.sw + row);
   }
+  // second label of a Mixup pair (cls/custom.py:116-117): same rules, weight (1 - lam); the first gets lam
+  const bool dual = MODE == 0 && a.label_b != nullptr;
+  int ybi = -1;
+  float gb = 0.f;
+  if (dual) {
+    const int64_t yb = active ? __ldg(a.label_b + row) : -1;
+    const bool yb_in = active && yb >= 0 && yb < C;
+    ybi = yb_in ? (int)yb : -1;
+    if (yb_in && yb != a.ignore_index) {
+      gb = a.scale * (1.f - a.lam);
+      if (a.cw) gb *= __ldg(a.cw + yb);
+      if (a.sw) gb *= __ldg(a.sw + row);
+    }
+    g *= a.lam;
+  }
 
   // ---- loads
   float4 z4[NQ], s4[CACHE_S ? NQ : 1];
@@ -187,7 +204,7 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
   };
 
   // ---- pass 1: row max of the adjusted logits, label's raw / adjusted logit, optional arg max
-  float m = -CUDART_INF_F, zy = -CUDART_INF_F, ay = 0.f;
+  float m = -CUDART_INF_F, zy = -CUDART_INF_F, ay = 0.f, ayb = 0.f;
   float bv = -CUDART_INF_F;
   int bi = 0x7fffffff;
 #pragma unroll
@@ -200,6 +217,8 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
       zy = d == 0 ? z4[q].x : (d == 1 ? z4[q].y : (d == 2 ? z4[q].z : z4[q].w));
       ay = d == 0 ? av.x : (d == 1 ? av.y : (d == 2 ? av.z : av.w));
     }
+    const unsigned db = (unsigned)(ybi - col);
+    if (db < 4u) ayb = db == 0 ? av.x : (db == 1 ? av.y : (db == 2 ? av.z : av.w));
     if (want_arg) {
       const float4 c4 = a.on_scaled ? av : z4[q];
       if (c4.x > bv) { bv = c4.x; bi = col; }
@@ -213,6 +232,7 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     zy = fmaxf(zy, __shfl_xor_sync(0xffffffffu, zy, o));
     ay += __shfl_xor_sync(0xffffffffu, ay, o);
+    if (dual) ayb += __shfl_xor_sync(0xffffffffu, ayb, o);
     if (want_arg) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -220,15 +240,18 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
     }
   }
   if constexpr (WPR > 1) {
-    if (lane == 0) { s_f[0][warp] = m; s_f[1][warp] = zy; s_f[2][warp] = bv; s_f[3][warp] = ay; s_i[warp] = bi; }
+    if (lane == 0) {
+      s_f[0][warp] = m; s_f[1][warp] = zy; s_f[2][warp] = bv; s_f[3][warp] = ay; s_f[4][warp] = ayb; s_i[warp] = bi;
+    }
     __syncthreads();
     hook();
-    m = s_f[0][w0]; zy = s_f[1][w0]; bv = s_f[2][w0]; ay = s_f[3][w0]; bi = s_i[w0];
+    m = s_f[0][w0]; zy = s_f[1][w0]; bv = s_f[2][w0]; ay = s_f[3][w0]; ayb = s_f[4][w0]; bi = s_i[w0];
 #pragma unroll
     for (int w = 1; w < WPR; ++w) {
       m = fmaxf(m, s_f[0][w0 + w]);
       zy = fmaxf(zy, s_f[1][w0 + w]);
       ay += s_f[3][w0 + w];
+      ayb += s_f[4][w0 + w];
       const float ov = s_f[2][w0 + w]; const int oi = s_i[w0 + w];
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
@@ -237,6 +260,7 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
     hook();
   }
   if (yi < 0) { zy = 0.f; ay = 0.f; }
+  if (ybi < 0) ayb = 0.f;
 
   if (raw_only) {
     float* o = a.out + (active ? row : 0) * a.ldo;
@@ -302,6 +326,7 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
     } else {
       const float lse = mm + logf(sum);
       my_loss = y_ok ? g * (lse - ay) : 0.f;
+      if (dual && gb != 0.f) my_loss += gb * (lse - ayb);
       if (active && t == 0) {
         if (a.loss_i) a.loss_i[row] = my_loss;
         if (a.lse) a.lse[row] = lse;
@@ -309,6 +334,7 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
       if (a.dz32 || a.dz16) {
         float* d32 = a.dz32 ? a.dz32 + (active ? row : 0) * a.lddz32 : nullptr;
         uint16_t* d16 = a.dz16 ? a.dz16 + (active ? row : 0) * a.lddz16 : nullptr;
+        const float ga = y_ok ? g : 0.f, gsum = ga + gb;          // dual: dz = s (G p - ga 1[ya] - gb 1[yb])
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           const int col = (q * TPR + t) * 4;
@@ -316,11 +342,20 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
             const float4 sv = sval(q);
             const unsigned dl = (unsigned)(yi - col);
             float4 d;
+            if (dual) {
+              const unsigned dlb = (unsigned)(ybi - col);
+              d.x = sv.x * (gsum * (z4[q].x * inv) - (dl == 0u ? ga : 0.f) - (dlb == 0u ? gb : 0.f));
+              d.y = sv.y * (gsum * (z4[q].y * inv) - (dl == 1u ? ga : 0.f) - (dlb == 1u ? gb : 0.f));
+              d.z = sv.z * (gsum * (z4[q].z * inv) - (dl == 2u ? ga : 0.f) - (dlb == 2u ? gb : 0.f));
+              d.w = sv.w * (gsum * (z4[q].w * inv) - (dl == 3u ? ga : 0.f) - (dlb == 3u ? gb : 0.f));
+              if (gsum == 0.f) d = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
             d.x = (sv.x * g) * (z4[q].x * inv - (dl == 0u ? 1.f : 0.f));
             d.y = (sv.y * g) * (z4[q].y * inv - (dl == 1u ? 1.f : 0.f));
             d.z = (sv.z * g) * (z4[q].z * inv - (dl == 2u ? 1.f : 0.f));
             d.w = (sv.w * g) * (z4[q].w * inv - (dl == 3u ? 1.f : 0.f));
             if (!y_ok) d = make_float4(0.f, 0.f, 0.f, 0.f);  // ignored row: exact zeros even for inf weights
+            }
             if (d32) stg_stream4(d32 + col, d);
             if (d16) stg_stream2(d16 + col, pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
           }

@@ -21,10 +21,12 @@ def _f32(t):
 
 class _IIFCrossEntropy(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, iif, target, class_weight, sample_weight, ignore_index, scale, reduce):
+    def forward(ctx, pred, iif, target, class_weight, sample_weight, ignore_index, scale, reduce, target_b=None,
+                lam=1.0):
         need = ctx.needs_input_grad[0]
         r = ops.softmax_ce(_f32(pred), iif, target, class_weight=class_weight, sample_weight=sample_weight,
-                           ignore_index=ignore_index, scale=scale, want_dz_f32=need, want_sum=reduce)
+                           ignore_index=ignore_index, scale=scale, want_dz_f32=need, want_sum=reduce,
+                           label_b=target_b, lam=lam)
         ctx.in_dtype = pred.dtype
         if need:
             ctx.save_for_backward(r["dz_f32"])
@@ -36,13 +38,15 @@ class _IIFCrossEntropy(torch.autograd.Function):
         out = ops.scale_rows(dz, g) if dz.numel() else dz
         if ctx.in_dtype != torch.float32:
             out = out.to(ctx.in_dtype)
-        return out, None, None, None, None, None, None, None
+        return out, None, None, None, None, None, None, None, None, None
 
 
 def iif_cross_entropy(pred, iif, target, *, class_weight=None, sample_weight=None, ignore_index=-100,
-                      scale=1.0, reduce=True):
-    """scale * sum_i w_i cw[y_i] CE(pred_i * iif, y_i)  (reduce=True) or the per-sample vector."""
-    return _IIFCrossEntropy.apply(pred, iif, target, class_weight, sample_weight, ignore_index, scale, reduce)
+                      scale=1.0, reduce=True, target_b=None, lam=1.0):
+    """scale * sum_i w_i cw[y_i] CE(pred_i * iif, y_i)  (reduce=True) or the per-sample vector.
+    With `target_b`: the Mixup pair lam*CE(target) + (1-lam)*CE(target_b) from one pass over the logits."""
+    return _IIFCrossEntropy.apply(pred, iif, target, class_weight, sample_weight, ignore_index, scale, reduce,
+                                  target_b, lam)
 
 
 class _SigmoidBCE(torch.autograd.Function):

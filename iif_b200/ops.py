@@ -137,9 +137,16 @@ def pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+class Unsupported(RuntimeError):
+    """The kernel does not cover this shape / alignment (IIF_EUNSUPPORTED): the caller picks another path."""
+
+
 def softmax_ce(z, iif, label, *, class_weight=None, sample_weight=None, ignore_index=-100, scale=1.0,
-               want_dz_f32=True, want_dz_bf16=False, want_acc=False, want_sum=True, want_lse=False):
-    """Returns dict(loss_i, loss_sum, dz_f32, dz_bf16 [B,pad8(C)], argmax, rank, acc_counts, lse)."""
+               want_dz_f32=True, want_dz_bf16=False, want_acc=False, want_sum=True, want_lse=False,
+               label_b=None, lam=1.0):
+    """Returns dict(loss_i, loss_sum, dz_f32, dz_bf16 [B,pad8(C)], argmax, rank, acc_counts, lse).
+    With `label_b`: the dual-label Mixup loss lam*CE(label) + (1-lam)*CE(label_b) in one pass
+    (raises `Unsupported` when the 128-bit path does not apply)."""
     z = _rows(z, "z", torch.float32)
     B, Cc = z.shape
     dev = z.device
@@ -158,6 +165,18 @@ def softmax_ce(z, iif, label, *, class_weight=None, sample_weight=None, ignore_i
     if B == 0:
         return r
     tk = loss_scratch(dev, B)
+    if label_b is not None:
+        if want_lse:
+            raise ValueError("want_lse is not available with label_b")
+        label_b = _vec(label_b, "label_b", B, torch.int64)
+        rc = _lib.load().iif_softmax_ce_mixup_fwd_bwd(
+            _ptr(z), _ld(z), _ptr(iif), _ptr(label), _ptr(label_b), float(lam), _ptr(cw), _ptr(sw), int(ignore_index),
+            float(scale), B, Cc, _ptr(r["loss_i"]), _ptr(r["loss_sum"]), _ptr(r["dz_f32"]), Cc, _ptr(r["dz_bf16"]),
+            pad8(Cc), _ptr(r["argmax"]), _ptr(r["rank"]), _ptr(r["acc_counts"]), _ptr(tk), _stream(dev))
+        if rc == _lib.EUNSUPPORTED:
+            raise Unsupported("softmax_ce_mixup: needs C % 4 == 0 and 16-byte aligned rows")
+        _lib.check(rc, "softmax_ce_mixup_fwd_bwd")
+        return r
     _lib.check(_lib.load().iif_softmax_ce_fwd_bwd(
         _ptr(z), _ld(z), _ptr(iif), _ptr(label), _ptr(cw), _ptr(sw), int(ignore_index), float(scale), B, Cc,
         _ptr(r["loss_i"]), _ptr(r["loss_sum"]), _ptr(r["dz_f32"]), Cc, _ptr(r["dz_bf16"]), pad8(Cc), _ptr(r["lse"]),

@@ -117,6 +117,17 @@ IIF_API int iif_softmax_ce_fwd_bwd(const float* z, int64_t ldz, const float* iif
                            int32_t* acc_counts, int32_t* scratch, void* stream);
 IIF_API size_t iif_loss_scratch_bytes(int64_t B);
 
+/* Dual-label (Mixup) form: loss_i = scale * [lam * l_i(label_a) + (1 - lam) * l_i(label_b)] with l_i as above,
+ * dz its gradient -- ONE pass over the logits where cls/custom.py:116-117 (Mixup.mixup_criterion) runs the
+ * criterion twice.  argmax / rank refer to label_a.  Needs the 128-bit path (C % 4 == 0, aligned rows):
+ * returns IIF_EUNSUPPORTED otherwise and the caller evaluates the two terms separately. */
+IIF_API int iif_softmax_ce_mixup_fwd_bwd(const float* z, int64_t ldz, const float* iif, const int64_t* label_a,
+                                 const int64_t* label_b, float lam, const float* class_weight,
+                                 const float* sample_weight, int64_t ignore_index, float scale, int64_t B,
+                                 int64_t C, float* loss_i, float* loss_sum, float* dz_f32, int64_t lddz_f32,
+                                 void* dz_bf16, int64_t lddz_bf16, int32_t* argmax, int32_t* rank,
+                                 int32_t* acc_counts, int32_t* scratch, void* stream);
+
 /* out = softmax(z * iif) per row (seg/mmdet/models/losses/iif_loss.py:76) or, with
  * softmax == 0, out = z * iif (cls/custom.py:38, infer=True).  argmax/rank (optional) are taken
  * on the ADJUSTED logits here (cls/train.py:104-106). */

@@ -157,6 +157,15 @@ def softmax_ce(z, iif, label, class_weight=None, sample_weight=None, ignore_inde
     return loss_i, dz, lse
 
 
+def mixup_ce(z, iif, label_a, label_b, lam, class_weight=None, sample_weight=None, ignore_index=-100):
+    """Mixup.mixup_criterion (cls/custom.py:116-117): lam * criterion(pred, y_a) + (1 - lam) * criterion(pred, y_b),
+    i.e. the same linear combination of the per-sample losses and of their gradients.
+    Returns (loss_i [B], dz [B,C]); the caller applies the reduction scale."""
+    la, da, _ = softmax_ce(z, iif, label_a, class_weight, sample_weight, ignore_index)
+    lb, db, _ = softmax_ce(z, iif, label_b, class_weight, sample_weight, ignore_index)
+    return lam * la + (1.0 - lam) * lb, lam * da + (1.0 - lam) * db
+
+
 def reduce_cls(loss_i, reduction):
     """cls/custom.py:32-36: plain mean / sum / per-sample vector. Returns (value, dscale)."""
     B = loss_i.shape[0]

@@ -50,6 +50,36 @@ def lt_labels(counts, n, gen):
     return torch.multinomial(p / p.sum(), n, replacement=True, generator=gen)
 
 
+# ------------------------------------------------------------------ classification Mixup (custom.py:91-117)
+def gen_cls_mixup():
+    """custom.Mixup.mixup_criterion around custom.IIFLoss: lam*CE(y_a) + (1-lam)*CE(y_b), loss and d/dlogits,
+    on a 4-divisible class count (the fused kernel's path) with a long-tailed profile."""
+    g = torch.Generator().manual_seed(7)
+    C, B = 100, 96
+    counts = [max(int(500 * (0.01) ** (c / (C - 1.0))), 1) for c in range(C)]
+    z0 = torch.randn(B, C, generator=g) * 2.0
+    y_a = lt_labels(counts, B, g)
+    y_b = y_a[torch.randperm(B, generator=g)]
+    cw = torch.tensor(counts, dtype=torch.float32)
+    cw = cw.sum() / cw
+    out = dict(counts=np.array(counts), z=npy(z0), y_a=npy(y_a), y_b=npy(y_b), cw=npy(cw))
+    for variant in ("raw", "smooth"):
+        for reduction in ("mean", "sum"):
+            for use_cw in (False, True):
+                for lam in (0.3, 1.0):
+                    crit = custom.IIFLoss(_DS(counts), variant=variant, reduction=reduction, device="cpu",
+                                          weight=cw if use_cw else None)
+                    mix = custom.Mixup(crit, alpha=0.2)
+                    z = z0.clone().requires_grad_(True)
+                    loss = mix.mixup_criterion(z, y_a, y_b, lam)
+                    loss.backward()
+                    tag = f"{variant}_{reduction}_{'cw' if use_cw else 'nocw'}_{lam}"
+                    out[f"loss_{tag}"] = npy(loss)
+                    out[f"dz_{tag}"] = npy(z.grad)
+    np.savez_compressed(os.path.join(HERE, "cls_mixup.npz"), **out)
+    print("cls_mixup.npz", len(out), "arrays")
+
+
 # ------------------------------------------------------------------ classification IIFLoss
 def gen_cls_iif():
     g = torch.Generator().manual_seed(0)
@@ -228,6 +258,7 @@ def gen_tables():
 if __name__ == "__main__":
     torch.set_num_threads(1)
     gen_cls_iif()
+    gen_cls_mixup()
     gen_cls_bce()
     gen_mmdet()
     gen_mmdet_bce()

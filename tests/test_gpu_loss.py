@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import head_oracle as ho
-from _common import TOL_F32, TOL_BF16, rel_err, head_inputs, iif_row, lt_counts
+from _common import TOL_F32, TOL_BF16, rel_err, head_inputs, iif_row, lt_counts, lt_labels
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -214,3 +214,77 @@ def test_full_size_properties(ops):
     assert float(r["loss_sum"]) == pytest.approx(float(r["loss_i"].double().sum()), rel=1e-6)
     assert torch.equal(r["rank"] == 0, r["argmax"].long() == y)
     assert torch.equal(r["argmax"].long(), z.argmax(1))
+
+
+# ------------------------------------------------------------------ Mixup: both labels in ONE pass
+@pytest.mark.parametrize("variant", ["raw", "smooth"])
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+@pytest.mark.parametrize("use_cw", [False, True])
+@pytest.mark.parametrize("lam", [0.3, 1.0])
+def test_mixup_fused_golden(ops, golden, variant, reduction, use_cw, lam):
+    """iif_softmax_ce_mixup_fwd_bwd against custom.Mixup.mixup_criterion(custom.IIFLoss) of the unmodified
+    reference (tests/golden/cls_mixup.npz)."""
+    g = golden("cls_mixup")
+    iif = ho.to_f32_row(ho.iif_weights_from_counts(g["counts"])[variant])
+    B = g["z"].shape[0]
+    scale = 1.0 / B if reduction == "mean" else 1.0
+    r = ops.softmax_ce(T(g["z"]), T(iif), T(g["y_a"]), label_b=T(g["y_b"]), lam=lam,
+                       class_weight=T(g["cw"]) if use_cw else None, scale=scale)
+    tag = f"{variant}_{reduction}_{'cw' if use_cw else 'nocw'}_{lam}"
+    assert float(r["loss_sum"]) == pytest.approx(float(g[f"loss_{tag}"]), rel=TOL_F32)
+    assert rel_err(N(r["dz_f32"]), g[f"dz_{tag}"]) < TOL_F32
+
+
+@pytest.mark.parametrize("B,C", [(256, 1000), (4096, 1204), (300, 8), (64, 10000)])
+def test_mixup_fused_vs_oracle_and_module(ops, B, C):
+    """Dual-label pass vs the oracle (ignored labels, sample weights), bf16 dZ, and the classification
+    mirror: Mixup.mixup_criterion(IIFLoss) takes the fused path and back-propagates like two calls."""
+    rng = np.random.default_rng(B + C)
+    counts = lt_counts(C)
+    z = (rng.standard_normal((B, C)) * 3).astype(np.float32)
+    ya, yb = lt_labels(counts, B, rng), lt_labels(counts, B, rng)
+    ya[::9] = -100
+    yb[5::11] = -100
+    sw = rng.uniform(0.5, 2.0, B).astype(np.float32)
+    iif = iif_row(counts, "smooth")
+    lam = 0.37
+    li, dz = ho.mixup_ce(z, iif, ya, yb, lam, sample_weight=sw)
+    r = ops.softmax_ce(T(z), T(iif), T(ya), label_b=T(yb), lam=lam, sample_weight=T(sw), scale=1.0 / B,
+                       want_dz_bf16=True)
+    assert rel_err(N(r["loss_i"]), li / B) < TOL_F32
+    assert float(r["loss_sum"]) == pytest.approx(li.sum() / B, rel=TOL_F32)
+    assert rel_err(N(r["dz_f32"]), dz / B) < TOL_F32
+    assert rel_err(N(r["dz_bf16"])[:, :C], dz / B) < 8e-3
+    # C % 4 != 0: the kernel declines, the mirror falls back to two passes
+    with pytest.raises(ops.Unsupported):
+        ops.softmax_ce(T(z[:, :C - 1].copy()), T(iif[:, :C - 1].copy()), T(np.clip(ya, -100, C - 2)),
+                       label_b=T(np.clip(yb, -100, C - 2)), lam=lam)
+
+
+def test_mixup_module_path():
+    from iif_b200.classification import IIFLoss, Mixup
+
+    class DS:
+        def get_cls_num_list(self):
+            return lt_counts(100).tolist()
+    rng = np.random.default_rng(1)
+    z = (rng.standard_normal((64, 100)) * 2).astype(np.float32)
+    ya, yb = lt_labels(lt_counts(100), 64, rng), lt_labels(lt_counts(100), 64, rng)
+    crit = IIFLoss(DS(), variant="smooth", device=DEV)
+    mix = Mixup(crit, alpha=0.2)
+    z1 = T(z).requires_grad_(True)
+    l1 = mix.mixup_criterion(z1, T(ya), T(yb), 0.25)              # fused
+    l1.backward()
+    z2 = T(z).requires_grad_(True)
+    l2 = 0.25 * crit(z2, T(ya)) + 0.75 * crit(z2, T(yb))          # the reference's two calls
+    l2.backward()
+    assert float(l1) == pytest.approx(float(l2), rel=1e-6)
+    assert rel_err(N(z1.grad), N(z2.grad)) < 1e-6
+    z3 = T(z[:, :99].copy()).requires_grad_(True)                  # 99 classes: falls back, still correct
+    class DS99:
+        def get_cls_num_list(self):
+            return lt_counts(100).tolist()[:99]
+    mix99 = Mixup(IIFLoss(DS99(), variant="raw", device=DEV))
+    l3 = mix99.mixup_criterion(z3, T(np.clip(ya, 0, 98)), T(np.clip(yb, 0, 98)), 0.5)
+    l3.backward()
+    assert np.isfinite(float(l3)) and z3.grad is not None

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import head_oracle as ho
-from _common import TOL_F32, TOL_BF16, rel_err, head_inputs, iif_row, bf16_round
+from _common import TOL_F32, TOL_BF16, rel_err, head_inputs, iif_row, bf16_round, lt_labels
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -348,3 +348,51 @@ def test_head_step_eager_back_to_back_rotating_sets():
     torch.cuda.synchronize()
     for hs, (l0, dw0, dx0, z0) in zip(sets, first):
         assert float(hs.loss) == l0 and torch.equal(hs.dw, dw0) and torch.equal(hs.dx, dx0) and torch.equal(hs.z, z0)
+
+
+def test_head_pipeline_host_batches():
+    """ops.HeadPipeline (iif_pipeline_*): steps fed from pinned HOST batches through the three-stream pipeline
+    return exactly the loss / gradients of the same step run directly on device tensors, slots are reused
+    safely (more batches than slots), and host tensors of the wrong kind are rejected."""
+    from iif_b200.ops import HeadStep, HeadPipeline
+    B, D, C = 256, 512, 1000
+    bf = torch.bfloat16
+    x0, w, b, counts, y0 = head_inputs(B, D, C, seed=3)
+    iif = T(iif_row(counts, "smooth")).reshape(-1)
+    wt, bt = T(w, bf), T(b)
+    nslots, nbatch = 3, 8
+    slots = []
+    for _ in range(nslots):
+        hs = HeadStep(B, D, C, DEV, want_acc=True)
+        hs.bind(torch.zeros(B, D, dtype=bf, device=DEV), wt, bt, iif, torch.zeros(B, dtype=torch.int64, device=DEV))
+        slots.append(hs)
+    pipe = HeadPipeline(slots)
+    rng = np.random.default_rng(0)
+    hx = [torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32)).to(bf).pin_memory() for _ in range(nbatch)]
+    hy = [torch.from_numpy(lt_labels(counts, B, rng)).pin_memory() for _ in range(nbatch)]
+    ref = HeadStep(B, D, C, DEV, want_acc=True)
+    want = []
+    for i in range(nbatch):
+        ref.bind(hx[i].to(DEV), wt, bt, iif, hy[i].to(DEV))
+        ref.launch()
+        torch.cuda.synchronize()
+        want.append((float(ref.loss), ref.dw.clone(), ref.dx.clone(), ref.acc_counts.clone()))
+    got = []
+    for i in range(nbatch):
+        k = i % nslots
+        if i >= nslots:
+            got.append((pipe.wait(k), slots[k].dw.clone(), slots[k].dx.clone(), slots[k].acc_counts.clone()))
+            torch.cuda.synchronize()                  # the copies above run on torch's stream, the pipeline on its own
+        pipe.submit(k, hx[i], hy[i])
+    for i in range(nbatch - nslots, nbatch):
+        k = i % nslots
+        got.append((pipe.wait(k), slots[k].dw.clone(), slots[k].dx.clone(), slots[k].acc_counts.clone()))
+    pipe.sync()
+    assert len(got) == nbatch
+    for (l, dw, dx, acc), (l0, dw0, dx0, acc0) in zip(got, want):
+        assert l == l0 and torch.equal(dw, dw0) and torch.equal(dx, dx0) and torch.equal(acc, acc0)
+    with pytest.raises(RuntimeError):
+        pipe.submit(0, hx[0].to(DEV), hy[0])          # device tensor where a host batch is expected
+    with pytest.raises(ValueError):
+        pipe.submit(0, hx[0].float(), hy[0])
+    pipe.close()

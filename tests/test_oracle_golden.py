@@ -269,3 +269,20 @@ def test_torch_port_mmdet(golden):
                      sample_weight=torch.from_numpy(g["w"]), avg_factor=float(g["avg_factor"]))
     close(r["loss"].numpy(), g["loss_raw_avg"])
     close(r["dx"].numpy()[:8], g["dz_raw_avg"])                       # W = I: dX is dZ
+
+
+# ------------------------------------------------------------------ Mixup (dual-label) loss
+@pytest.mark.parametrize("variant", ["raw", "smooth"])
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+@pytest.mark.parametrize("use_cw", [False, True])
+@pytest.mark.parametrize("lam", [0.3, 1.0])
+def test_mixup_golden(golden, variant, reduction, use_cw, lam):
+    """custom.Mixup.mixup_criterion around custom.IIFLoss (unmodified reference) vs the oracle's mixup_ce."""
+    g = golden("cls_mixup")
+    iif = ho.to_f32_row(ho.iif_weights_from_counts(g["counts"])[variant])
+    cw = g["cw"] if use_cw else None
+    loss_i, dz = ho.mixup_ce(g["z"], iif, g["y_a"], g["y_b"], lam, class_weight=cw)
+    val, scale = ho.reduce_cls(loss_i, reduction)
+    tag = f"{variant}_{reduction}_{'cw' if use_cw else 'nocw'}_{lam}"
+    close(val, g[f"loss_{tag}"])
+    close(dz * scale, g[f"dz_{tag}"])
