@@ -48,6 +48,8 @@ SIGNATURES = {
     "iif_scaled_activation": (_i32, [_p, _i64, _p, _i32, _i64, _i64, _p, _i64, _p, _p, _p, _p]),
     "iif_sigmoid_bce_fwd_bwd": (_i32, [_p, _i64, _p, _p, _p, _p, _i64, _f32, _i64, _i64, _p, _i64, _p, _p, _p, _i64,
                                        _p, _i64, _p, _p]),
+    "iif_sigmoid_focal_fwd_bwd": (_i32, [_p, _i64, _p, _f32, _f32, _p, _p, _i64, _f32, _i64, _i64, _p, _i64, _p, _p, _p, _i64,
+                                         _p, _i64, _p, _p]),
     "iif_scale_rows": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _p, _i32, _i64, _p]),
     "iif_colsum": (_i32, [_p, _i32, _i64, _p, _i64, _i64, _p, _p]),
     "iif_linear_fwd_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p, _sz, _p]),

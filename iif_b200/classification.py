@@ -1,4 +1,4 @@
-"""Drop-in for classification/custom.py: IIFLoss, FocalLoss(gamma=0) and the accuracy helper.
+"""Drop-in for classification/custom.py: IIFLoss, FocalLoss, Mixup and the accuracy helper.
 
 Same constructor / forward signatures, attribute names (`.iif`, `.variant`, `.reduction`) and
 reductions as the reference; the arithmetic runs in the fused CUDA kernels (no torch ops on the
@@ -58,15 +58,14 @@ class IIFLoss(nn.Module):
 
 
 class FocalLoss(nn.Module):
-    """classification/custom.py:42-89, gamma == 0 branch (= sigmoid BCE, `--classif bce`).
-
-    The one-hot target tensor of the reference (:61-63) is never built.  gamma > 0 (the focal
-    branch, :74-89) is outside the IIF hot path and not provided."""
+    """classification/custom.py:42-89: gamma == 0 is sigmoid BCE (`--classif bce`), gamma > 0 the focal
+    branch with optional alpha balance (:74-89).  The one-hot target tensor of the reference (:61-63) is
+    never built; the focal branch is evaluated in logit space (softplus) instead of sigmoid -> log in fp32."""
 
     def __init__(self, gamma, alpha=None, reduction="mean", device="cuda", weights=None):
         super().__init__()
-        if gamma != 0:
-            raise NotImplementedError("iif_b200.FocalLoss implements the gamma == 0 (sigmoid BCE) branch only")
+        if gamma < 0:
+            raise ValueError("gamma must be >= 0")
         self.gamma, self.alpha, self.reduction = gamma, alpha, reduction
         self.weights = weights.unsqueeze(0) if weights is not None else 1
 
@@ -76,9 +75,10 @@ class FocalLoss(nn.Module):
     def forward(self, pred, targets):
         B, C = pred.shape
         colw = None if isinstance(self.weights, int) else self.weights.reshape(-1)
-        # 'sum' -> sum / B ; anything else -> mean over B*C (custom.py:67-70)
+        # 'sum' -> sum / B ; anything else -> mean over B*C (custom.py:67-70, 84-88)
         scale = 1.0 / max(B, 1) if self.reduction == "sum" else 1.0 / max(B * C, 1)
-        return F_.sigmoid_bce(pred, targets, col_weight=colw, scale=scale)
+        return F_.sigmoid_bce(pred, targets, col_weight=colw, scale=scale, gamma=float(self.gamma),
+                              alpha=self.alpha if self.alpha else None)
 
 
 class Mixup(object):

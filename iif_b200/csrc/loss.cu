@@ -117,6 +117,7 @@ struct BceArgs {
   int64_t ignore_index; float scale; int64_t B; int C;
   float* loss_elem; int64_t ldl; float* loss_i; float* loss_sum;
   float* dz32; int64_t lddz32; uint16_t* dz16; int64_t lddz16; int32_t* scratch;
+  float gamma, alpha;                  // focal modulation (gamma > 0) and class balance (alpha > 0), cls/custom.py:74-89
 };
 
 __device__ __forceinline__ void bce_elem(float z, bool t, float pw, float wgt, float& loss, float& d) {
@@ -127,6 +128,28 @@ __device__ __forceinline__ void bce_elem(float z, bool t, float pw, float wgt, f
   loss = wgt * ((t ? 0.f : z) + lw * sp);
   const float sig = z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
   d = wgt * ((t ? 0.f : 1.f) - lw * (1.f - sig));
+}
+
+// Focal branch of cls/custom.py:74-89 in logit space (the reference goes sigmoid -> BCELoss -> pow in fp32):
+//   q = p_t = t p + (1-t)(1-p),  L = -log(q) (1-q)^gamma * alpha_t,
+//   t = 1: L = sp(-z) e^{-gamma sp(z)},  dL/dz = -(1-p)^gamma [(1-p) + gamma p sp(-z)]
+//   t = 0: L = sp(z) e^{-gamma sp(-z)},  dL/dz =  p^gamma [p + gamma (1-p) sp(z)]        (sp = softplus)
+__device__ __forceinline__ void focal_elem(float z, bool t, float gamma, float alpha, float wgt, float& loss, float& d) {
+  const float e = expf(-fabsf(z));
+  const float l1 = log1pf(e);
+  const float sp_pos = l1 + fmaxf(z, 0.f), sp_neg = l1 + fmaxf(-z, 0.f);   // softplus(z), softplus(-z)
+  const float p = z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+  const float at = alpha > 0.f ? (t ? alpha : 1.f - alpha) : 1.f;
+  const float w = wgt * at;
+  if (t) {
+    const float mod = expf(-gamma * sp_pos);        // (1-p)^gamma
+    loss = w * sp_neg * mod;
+    d = -w * mod * ((1.f - p) + gamma * p * sp_neg);
+  } else {
+    const float mod = expf(-gamma * sp_neg);        // p^gamma
+    loss = w * sp_pos * mod;
+    d = w * mod * (p + gamma * (1.f - p) * sp_pos);
+  }
 }
 
 template <bool VEC>
@@ -158,10 +181,17 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
         float4 p4 = make_float4(1.f, 1.f, 1.f, 1.f), c4 = p4, l4, d4;
         if (a.pw) p4 = __ldg(reinterpret_cast<const float4*>(a.pw + col));
         if (a.colw) c4 = __ldg(reinterpret_cast<const float4*>(a.colw + col));
+        if (a.gamma > 0.f) {
+          focal_elem(z4.x, col + 0 == yi, a.gamma, a.alpha, wrow * c4.x, l4.x, d4.x);
+          focal_elem(z4.y, col + 1 == yi, a.gamma, a.alpha, wrow * c4.y, l4.y, d4.y);
+          focal_elem(z4.z, col + 2 == yi, a.gamma, a.alpha, wrow * c4.z, l4.z, d4.z);
+          focal_elem(z4.w, col + 3 == yi, a.gamma, a.alpha, wrow * c4.w, l4.w, d4.w);
+        } else {
         bce_elem(z4.x, col + 0 == yi, p4.x, wrow * c4.x, l4.x, d4.x);
         bce_elem(z4.y, col + 1 == yi, p4.y, wrow * c4.y, l4.y, d4.y);
         bce_elem(z4.z, col + 2 == yi, p4.z, wrow * c4.z, l4.z, d4.z);
         bce_elem(z4.w, col + 3 == yi, p4.w, wrow * c4.w, l4.w, d4.w);
+        }
         if (!valid) { l4 = make_float4(0.f, 0.f, 0.f, 0.f); d4 = l4; }
         acc += (l4.x + l4.y) + (l4.z + l4.w);
         if (le) stg_stream4(le + col, l4);
@@ -171,6 +201,9 @@ __global__ void __launch_bounds__(256) bce_kernel(const BceArgs a) {
     } else {
       for (int col = t; col < C; col += TPR) {
         float l, d;
+        if (a.gamma > 0.f)
+          focal_elem(__ldg(zr + col), col == yi, a.gamma, a.alpha, wrow * (a.colw ? __ldg(a.colw + col) : 1.f), l, d);
+        else
         bce_elem(__ldg(zr + col), col == yi, a.pw ? __ldg(a.pw + col) : 1.f,
                  wrow * (a.colw ? __ldg(a.colw + col) : 1.f), l, d);
         if (!valid) { l = 0.f; d = 0.f; }
@@ -288,11 +321,11 @@ extern "C" int iif_scaled_activation(const float* z, int64_t ldz, const float* i
   return dispatch_row<1>(a, vec, (cudaStream_t)stream);
 }
 
-extern "C" int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_t* label, const float* pos_weight,
-                                       const float* col_weight, const float* sample_weight, int64_t ignore_index,
-                                       float scale, int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
-                                       float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
-                                       int64_t lddz_bf16, int32_t* scratch, void* stream) {
+static int sigmoid_loss(const float* z, int64_t ldz, const int64_t* label, const float* pos_weight,
+                        const float* col_weight, const float* sample_weight, int64_t ignore_index,
+                        float scale, int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
+                        float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
+                        int64_t lddz_bf16, int32_t* scratch, void* stream, float gamma, float alpha) {
   if (B < 0 || C <= 0 || (B > 0 && (!z || !label)) || ldz < C) return IIF_EINVAL;
   if ((dz_f32 && lddz_f32 < C) || (dz_bf16 && lddz_bf16 < C) || (loss_elem && ldl < C)) return IIF_EINVAL;
   if (loss_sum && !scratch) return IIF_EINVAL;
@@ -303,6 +336,7 @@ extern "C" int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_
   a.ignore_index = ignore_index; a.scale = scale; a.B = B; a.C = (int)C; a.loss_elem = loss_elem; a.ldl = ldl;
   a.loss_i = loss_i; a.loss_sum = loss_sum; a.dz32 = dz_f32; a.lddz32 = lddz_f32;
   a.dz16 = reinterpret_cast<uint16_t*>(dz_bf16); a.lddz16 = lddz_bf16; a.scratch = scratch;
+  a.gamma = gamma; a.alpha = alpha;
   const bool vec = (C % 4 == 0) && (ldz % 4 == 0) && aligned16(z) && (!pos_weight || aligned16(pos_weight)) &&
                    (!col_weight || aligned16(col_weight)) && (!loss_elem || (aligned16(loss_elem) && ldl % 4 == 0)) &&
                    (!dz_f32 || (aligned16(dz_f32) && lddz_f32 % 4 == 0)) &&
@@ -312,6 +346,25 @@ extern "C" int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_
   if (vec) bce_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   else bce_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return launch_status();
+}
+
+extern "C" int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_t* label, const float* pos_weight,
+                                       const float* col_weight, const float* sample_weight, int64_t ignore_index,
+                                       float scale, int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
+                                       float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
+                                       int64_t lddz_bf16, int32_t* scratch, void* stream) {
+  return sigmoid_loss(z, ldz, label, pos_weight, col_weight, sample_weight, ignore_index, scale, B, C, loss_elem, ldl,
+                      loss_i, loss_sum, dz_f32, lddz_f32, dz_bf16, lddz_bf16, scratch, stream, 0.f, 0.f);
+}
+
+extern "C" int iif_sigmoid_focal_fwd_bwd(const float* z, int64_t ldz, const int64_t* label, float gamma, float alpha,
+                                         const float* col_weight, const float* sample_weight, int64_t ignore_index,
+                                         float scale, int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
+                                         float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
+                                         int64_t lddz_bf16, int32_t* scratch, void* stream) {
+  if (!(gamma > 0.f) || alpha >= 1.f) return IIF_EINVAL;
+  return sigmoid_loss(z, ldz, label, nullptr, col_weight, sample_weight, ignore_index, scale, B, C, loss_elem, ldl,
+                      loss_i, loss_sum, dz_f32, lddz_f32, dz_bf16, lddz_bf16, scratch, stream, gamma, alpha > 0.f ? alpha : 0.f);
 }
 
 extern "C" int iif_scale_rows(const float* in, int64_t ldi, const float* g, int64_t g_stride, int64_t rows, int64_t cols,

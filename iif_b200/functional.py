@@ -51,11 +51,13 @@ def iif_cross_entropy(pred, iif, target, *, class_weight=None, sample_weight=Non
 
 class _SigmoidBCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, target, pos_weight, col_weight, sample_weight, ignore_index, scale, mode):
+    def forward(ctx, pred, target, pos_weight, col_weight, sample_weight, ignore_index, scale, mode, gamma=0.0,
+                alpha=None):
         need = ctx.needs_input_grad[0]
         r = ops.sigmoid_bce(_f32(pred), target, pos_weight=pos_weight, col_weight=col_weight,
                             sample_weight=sample_weight, ignore_index=ignore_index, scale=scale,
-                            want_elem=(mode == "elem"), want_dz_f32=need, want_sum=(mode == "sum"))
+                            want_elem=(mode == "elem"), want_dz_f32=need, want_sum=(mode == "sum"), gamma=gamma,
+                            alpha=alpha)
         ctx.in_dtype, ctx.mode = pred.dtype, mode
         if need:
             ctx.save_for_backward(r["dz_f32"])
@@ -70,13 +72,14 @@ class _SigmoidBCE(torch.autograd.Function):
             out = dz * g
         if ctx.in_dtype != torch.float32:
             out = out.to(ctx.in_dtype)
-        return out, None, None, None, None, None, None, None
+        return out, None, None, None, None, None, None, None, None, None
 
 
 def sigmoid_bce(pred, target, *, pos_weight=None, col_weight=None, sample_weight=None, ignore_index=-100,
-                scale=1.0, reduce=True):
+                scale=1.0, reduce=True, gamma=0.0, alpha=None):
+    """Sigmoid BCE (gamma = 0) or focal loss (gamma > 0, optional alpha balance) with fused backward."""
     return _SigmoidBCE.apply(pred, target, pos_weight, col_weight, sample_weight, ignore_index, scale,
-                             "sum" if reduce else "elem")
+                             "sum" if reduce else "elem", gamma, alpha)
 
 
 class _Linear(torch.autograd.Function):

@@ -201,7 +201,8 @@ def scaled_activation(z, iif, softmax: bool, label=None, want_pred=False):
 
 
 def sigmoid_bce(z, label, *, pos_weight=None, col_weight=None, sample_weight=None, ignore_index=-100, scale=1.0,
-                want_elem=False, want_dz_f32=True, want_dz_bf16=False, want_sum=True):
+                want_elem=False, want_dz_f32=True, want_dz_bf16=False, want_sum=True, gamma=0.0, alpha=None):
+    """Sigmoid BCE forward + backward; gamma > 0 selects the focal form (cls/custom.py:74-89)."""
     z = _rows(z, "z", torch.float32)
     B, Cc = z.shape
     dev = z.device
@@ -215,6 +216,15 @@ def sigmoid_bce(z, label, *, pos_weight=None, col_weight=None, sample_weight=Non
     r["dz_f32"] = torch.empty(B, Cc, dtype=torch.float32, device=dev) if want_dz_f32 else None
     r["dz_bf16"] = torch.empty(B, pad8(Cc), dtype=torch.bfloat16, device=dev) if want_dz_bf16 else None
     if B == 0:
+        return r
+    if gamma and gamma > 0:
+        if pw is not None:
+            raise ValueError("pos_weight is not part of the focal form")
+        _lib.check(_lib.load().iif_sigmoid_focal_fwd_bwd(
+            _ptr(z), _ld(z), _ptr(label), float(gamma), float(alpha) if alpha else 0.0, _ptr(colw), _ptr(sw),
+            int(ignore_index), float(scale), B, Cc, _ptr(r["loss_elem"]), Cc, _ptr(r["loss_i"]), _ptr(r["loss_sum"]),
+            _ptr(r["dz_f32"]), Cc, _ptr(r["dz_bf16"]), pad8(Cc), _ptr(loss_scratch(dev, B)), _stream(dev)),
+            "sigmoid_focal_fwd_bwd")
         return r
     _lib.check(_lib.load().iif_sigmoid_bce_fwd_bwd(
         _ptr(z), _ld(z), _ptr(label), _ptr(pw), _ptr(colw), _ptr(sw), int(ignore_index), float(scale), B, Cc,

@@ -155,6 +155,17 @@ IIF_API int iif_sigmoid_bce_fwd_bwd(const float* z, int64_t ldz, const int64_t* 
                             float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
                             int64_t lddz_bf16, int32_t* scratch, void* stream);
 
+/* Focal form of the same kernel (cls FocalLoss with gamma > 0, cls/custom.py:74-89):
+ *   p = sigmoid(z), q = t p + (1-t)(1-p),  e_ic = -log(q) (1-q)^gamma * (alpha > 0 ? (t alpha + (1-t)(1-alpha)) : 1)
+ * with wgt / scale / outputs as above (no pos_weight).  Evaluated in logit space (softplus), so it stays
+ * accurate where the reference's fp32 sigmoid -> log saturates.  gamma must be > 0 (gamma = 0 is
+ * iif_sigmoid_bce_fwd_bwd), alpha <= 0 means "no class balance". */
+IIF_API int iif_sigmoid_focal_fwd_bwd(const float* z, int64_t ldz, const int64_t* label, float gamma, float alpha,
+                              const float* col_weight, const float* sample_weight, int64_t ignore_index,
+                              float scale, int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
+                              float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
+                              int64_t lddz_bf16, int32_t* scratch, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * small elementwise helpers on [rows, cols] matrices
  * ------------------------------------------------------------------------------------------- */

@@ -249,6 +249,29 @@ def sigmoid_bce_cls(z, label, weights=None):
     return loss * w, dz * w
 
 
+def focal_cls(z, label, gamma, alpha=None, weights=None):
+    """cls FocalLoss with gamma > 0 (cls/custom.py:74-84): p = sigmoid(z); BCELoss(p, onehot) * (1 - p_t)^gamma
+    * weights_c * alpha_t, with p_t = p t + (1-p)(1-t), alpha_t = alpha t + (1-alpha)(1-t) when alpha is set.
+    Exact arithmetic (float64, log-sigmoid via logaddexp); returns the elementwise loss [B,C] and d/dz."""
+    z = np.asarray(z, np.float64)
+    B, C = z.shape
+    t = np.zeros((B, C))
+    t[np.arange(B), np.asarray(label, np.int64)] = 1.0
+    logp, log1mp = -np.logaddexp(0.0, -z), -np.logaddexp(0.0, z)
+    p = np.exp(logp)
+    logq = np.where(t > 0, logp, log1mp)                 # log p_t
+    q = np.exp(logq)
+    mod = (1.0 - q) ** gamma
+    loss = -logq * mod
+    # d/dq [-log q (1-q)^g] = -(1-q)^g / q + g (1-q)^(g-1) log q ;  dq/dz = +-p(1-p) = +-q(1-q)
+    dq = -(1.0 - q) ** (gamma + 1.0) + gamma * q * mod * logq
+    dz = np.where(t > 0, dq, -dq)
+    w = 1.0 if weights is None else np.asarray(weights, np.float64)[None, :]
+    if alpha:
+        w = w * (alpha * t + (1.0 - alpha) * (1.0 - t))
+    return loss * w, dz * w
+
+
 # ----------------------------------------------------------------------------------------
 # a9  accuracy
 # ----------------------------------------------------------------------------------------

@@ -143,6 +143,32 @@ def gen_cls_bce():
     np.savez_compressed(os.path.join(HERE, "cls_bce.npz"), **out)
 
 
+def gen_cls_focal():
+    """custom.FocalLoss(gamma > 0) (custom.py:74-89).  The reference only runs in fp32 (its one-hot tensor is a
+    FloatTensor) and goes sigmoid -> log, so the logits are kept moderate (std 1.5): there its own chain is
+    accurate to ~1e-6 and pins the oracle; alpha on / off, per-class weights on / off."""
+    g = torch.Generator().manual_seed(2)
+    B, C = 48, 40
+    z0 = torch.randn(B, C, generator=g) * 1.5
+    y = torch.randint(0, C, (B,), generator=g)
+    wts = torch.rand(C, generator=g) + 0.5
+    out = dict(z=npy(z0), y=npy(y), weights=npy(wts))
+    with ref_loader.cpu_shims():
+        for gamma in (2.0, 0.5):
+            for alpha in (None, 0.25):
+                for red in ("mean", "sum"):
+                    for tag, ww in (("now", None), ("w", wts)):
+                        crit = custom.FocalLoss(gamma=gamma, alpha=alpha, reduction=red, device="cpu", weights=ww)
+                        z = z0.clone().requires_grad_(True)
+                        loss = crit(z, y)
+                        loss.backward()
+                        key = f"{gamma}_{alpha}_{tag}_{red}"
+                        out[f"loss_{key}"] = npy(loss)
+                        out[f"dz_{key}"] = npy(z.grad)
+    np.savez_compressed(os.path.join(HERE, "cls_focal.npz"), **out)
+    print("cls_focal.npz", len(out), "arrays")
+
+
 # ------------------------------------------------------------------ mmdet IIFLoss / FasaIIFLoss
 def gen_mmdet():
     g = torch.Generator().manual_seed(2)
@@ -260,6 +286,7 @@ if __name__ == "__main__":
     gen_cls_iif()
     gen_cls_mixup()
     gen_cls_bce()
+    gen_cls_focal()
     gen_mmdet()
     gen_mmdet_bce()
     gen_tables()

@@ -288,3 +288,37 @@ def test_mixup_module_path():
     l3 = mix99.mixup_criterion(z3, T(np.clip(ya, 0, 98)), T(np.clip(yb, 0, 98)), 0.5)
     l3.backward()
     assert np.isfinite(float(l3)) and z3.grad is not None
+
+
+# ------------------------------------------------------------------ focal loss (gamma > 0)
+@pytest.mark.parametrize("gamma,alpha", [(2.0, None), (2.0, 0.25), (0.5, 0.25)])
+@pytest.mark.parametrize("B,C", [(48, 40), (300, 1000), (64, 37)])
+def test_focal_vs_oracle(ops, gamma, alpha, B, C):
+    """iif_sigmoid_focal_fwd_bwd vs the float64 oracle (large logits included: the logit-space form stays
+    accurate where sigmoid -> log in fp32 does not), per-class weights, bf16 dZ, both load paths."""
+    rng = np.random.default_rng(B + C)
+    z = (rng.standard_normal((B, C)) * 4).astype(np.float32)
+    y = rng.integers(0, C, B).astype(np.int64)
+    w = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    loss, dz = ho.focal_cls(z, y, gamma, alpha, w)
+    scale = 1.0 / (B * C)
+    r = ops.sigmoid_bce(T(z), T(y), col_weight=T(w), scale=scale, gamma=gamma, alpha=alpha, want_elem=True,
+                        want_dz_bf16=True)
+    assert float(r["loss_sum"]) == pytest.approx(loss.sum() * scale, rel=TOL_F32)
+    assert rel_err(N(r["loss_elem"]), loss * scale) < TOL_F32
+    assert rel_err(N(r["dz_f32"]), dz * scale) < TOL_F32
+    assert rel_err(N(r["dz_bf16"])[:, :C], dz * scale) < 8e-3
+
+
+@pytest.mark.parametrize("red", ["mean", "sum"])
+def test_focal_golden_and_module(ops, golden, red):
+    """Against custom.FocalLoss(gamma=2, alpha=0.25) of the unmodified reference, through the classification mirror."""
+    from iif_b200.classification import FocalLoss
+    g = golden("cls_focal")
+    crit = FocalLoss(gamma=2.0, alpha=0.25, reduction=red, device=DEV, weights=T(g["weights"]))
+    z = T(g["z"]).requires_grad_(True)
+    loss = crit(z, T(g["y"]))
+    loss.backward()
+    key = f"2.0_0.25_w_{red}"
+    assert float(loss.detach()) == pytest.approx(float(g[f"loss_{key}"]), rel=3e-5)
+    assert rel_err(N(z.grad), g[f"dz_{key}"]) < 3e-5

@@ -96,8 +96,8 @@ def test_cls_focal_gamma0_and_accuracy(golden):
             assert float(loss) == pytest.approx(float(g[f"loss_{tag}_{red}"]), rel=TOL_F32)
             loss.backward()
             assert rel_err(N(z.grad), g[f"dz_{tag}_{red}"]) < TOL_F32
-    with pytest.raises(NotImplementedError):
-        FocalLoss(2.0)
+    with pytest.raises(ValueError):
+        FocalLoss(-1.0)
     c = golden("cls_iif")
     a1, a5 = accuracy(T(c["z"]), T(c["y"]), topk=(1, 5))
     e1, e5 = ho.topk_accuracy(c["z"], c["y"], (1, 5))

@@ -286,3 +286,19 @@ def test_mixup_golden(golden, variant, reduction, use_cw, lam):
     tag = f"{variant}_{reduction}_{'cw' if use_cw else 'nocw'}_{lam}"
     close(val, g[f"loss_{tag}"])
     close(dz * scale, g[f"dz_{tag}"])
+
+
+# ------------------------------------------------------------------ focal loss (gamma > 0)
+@pytest.mark.parametrize("gamma", [2.0, 0.5])
+@pytest.mark.parametrize("alpha", [None, 0.25])
+@pytest.mark.parametrize("red", ["mean", "sum"])
+@pytest.mark.parametrize("wtag", ["now", "w"])
+def test_focal_golden(golden, gamma, alpha, red, wtag):
+    """custom.FocalLoss(gamma > 0) of the unmodified reference (fp32, sigmoid -> BCELoss -> pow) vs ho.focal_cls."""
+    g = golden("cls_focal")
+    B, C = g["z"].shape
+    loss, dz = ho.focal_cls(g["z"], g["y"], gamma, alpha, g["weights"] if wtag == "w" else None)
+    scale = 1.0 / B if red == "sum" else 1.0 / (B * C)
+    key = f"{gamma}_{alpha}_{wtag}_{red}"
+    close(loss.sum() * scale, g[f"loss_{key}"], rtol=3e-5)
+    close(dz * scale, g[f"dz_{key}"], rtol=3e-5)
