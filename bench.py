@@ -116,6 +116,31 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+# DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+# ------------------------------------------------------------------------------------------------
+def ncu_traffic(kernel, shape):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) of `kernel` for the ImageNet-LT shape,
+    from profiles/r1_ncu_head_full_summary.csv (tools/gpu_profile.sh); None when there is no capture."""
+    import csv
+    grid = {"linear_fwd_bf16": "128", "loss_linear_bwd_bf16": "256"}.get(kernel)
+    path = os.path.join(ROOT, "profiles", "r1_ncu_head_full_summary.csv")
+    if shape != (256, 2048, 1000) or grid is None or not os.path.exists(path):
+        return None, None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    with open(path) as fh:
+        rows = list(csv.reader(fh))
+    hdr, units = rows[0], rows[1]
+    try:
+        ir, iw, ig = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("launch__grid_size")
+        vals = [float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]] for r in rows[2:] if r[ig] == grid]
+    except (ValueError, KeyError, IndexError):
+        return None, None
+    if not vals:
+        return None, None
+    return sum(vals) / len(vals), f"profiles/r1_ncu_head_full_summary.csv ({len(vals)} launches, ncu --set full, cold caches)"
+
+
+# ------------------------------------------------------------------------------------------------
 # CPU arm
 # ------------------------------------------------------------------------------------------------
 def cpu_arm(B, D, C, seconds, steps=None, warmup=3):
@@ -404,6 +429,8 @@ def main():
                     "step_roofline_us": sum(max(k["algo_bytes"] / (pk["hbm"] * 1e9), k["flops"] / (pk["tf_sust"] * 1e12))
                                             for k in kern) * 1e6}
         roofline["step_frac"] = roofline["step_roofline_us"] / (ms * 1e3 / args.steps)
+        roofline["traffic"], roofline["traffic_source"] = ncu_traffic(top["kernel"], (B, D, C))
+        roofline["algo_bytes"] = top["algo_bytes"]
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_arm(B, D, C, args.cpu_seconds)

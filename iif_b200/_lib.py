@@ -15,6 +15,7 @@ OK, EINVAL, EALIGN, EUNSUPPORTED, EWORKSPACE, EDRIVER = 0, -1, -2, -3, -4, -5
 VARIANT_IDS = {"raw": 0, "smooth": 1, "rel": 2, "prob": 2, "normit": 3, "gombit": 4, "base2": 5, "base10": 6}
 DTYPE_F32, DTYPE_BF16 = 0, 1
 HEAD_NO_FUSED_LOSS = 1
+NORM_NORMED, NORM_COS, NORM_UNIT = 0, 1, 2
 
 _p, _i64, _i32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t
 
@@ -50,6 +51,9 @@ SIGNATURES = {
                                        _p, _i64, _p, _p]),
     "iif_sigmoid_focal_fwd_bwd": (_i32, [_p, _i64, _p, _f32, _f32, _p, _p, _i64, _f32, _i64, _i64, _p, _i64, _p, _p, _p, _i64,
                                          _p, _i64, _p, _p]),
+    "iif_row_scale_from_norm": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _f32, _f32, _f32, _p, _p, _p, _p]),
+    "iif_row_dot": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _p, _p]),
+    "iif_rows_axpby": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _p, _i64, _p]),
     "iif_scale_rows": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _p, _i32, _i64, _p]),
     "iif_colsum": (_i32, [_p, _i32, _i64, _p, _i64, _i64, _p, _p]),
     "iif_linear_fwd_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p, _sz, _p]),

@@ -107,6 +107,31 @@ class Mixup(object):
         return lam * self.criterion(pred, y_a) + (1 - lam) * self.criterion(pred, y_b)
 
 
+class CosNorm_Classifier(nn.Module):
+    """classification/resnet_cifar.py:50-78: z = scale * (x / (1 + |x|)) . (w / |w|)^T  (no bias).  The two
+    operand normalisations and their backward run in the library's row kernels, the contraction in the head's
+    GEMMs (`compute` = 'bf16' tensor cores | 'fp32').  `lr_scale=True` (a learnable scale, squared) is not
+    provided."""
+
+    def __init__(self, in_dims, out_dims, scale=16, margin=0.5, init_std=0.001, lr_scale=False, compute="bf16",
+                 device="cuda"):
+        super().__init__()
+        if lr_scale:
+            raise NotImplementedError("CosNorm_Classifier(lr_scale=True) is not provided")
+        import math
+        self.in_features, self.out_dims, self.lr_scale = in_dims, out_dims, lr_scale
+        self.scale, self.margin, self.compute = scale, margin, compute
+        self.weight = nn.Parameter(torch.empty(out_dims, in_dims, device=device))
+        stdv = 1.0 / math.sqrt(in_dims)
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def forward(self, input, *args):
+        from . import _lib
+        ex = F_.normalize_rows(input, _lib.NORM_COS, temperature=float(self.scale))
+        ew = F_.normalize_rows(self.weight, _lib.NORM_UNIT, temperature=1.0, eps=0.0)
+        return F_.linear(ex, ew, None, bf16=(self.compute == "bf16"))
+
+
 def accuracy(output, target, topk=(1,)):
     """classification/utils.py:165-179: top-k hit rate x 100/B, one fused pass (rank of the label)."""
     with torch.no_grad():

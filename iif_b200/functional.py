@@ -82,6 +82,36 @@ def sigmoid_bce(pred, target, *, pos_weight=None, col_weight=None, sample_weight
                              "sum" if reduce else "elem", gamma, alpha)
 
 
+class _NormalizeRows(torch.autograd.Function):
+    """y_i = pre_i r(|pre_i x_i|) x_i -- the operand normalisation of the normalised classifiers
+    (mmdet normed_predictor.py:36-40,70-76; cls/resnet_cifar.py:66-71) with its exact backward
+    dx_i = a_i g_i + c_i (x_i . g_i) x_i, all in the library's row kernels (csrc/norm.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, pre, mode, temperature, power, eps):
+        x2 = _f32(x.reshape(-1, x.shape[-1]))
+        need = ctx.needs_input_grad[0]
+        a, c = ops.row_scale_from_norm(x2, mode, pre=pre, temperature=temperature, power=power, eps=eps, want_c=need)
+        y = ops.rows_axpby(x2, a)
+        if need:
+            ctx.save_for_backward(x2, a, c)
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, a, c = ctx.saved_tensors
+        g2 = _f32(g.reshape(-1, g.shape[-1]))
+        dot = ops.row_dot(x2, g2)
+        dx = ops.rows_axpby(g2, a, x2, c, dot)
+        return dx.to(ctx.x_dtype).reshape(ctx.x_shape), None, None, None, None, None
+
+
+def normalize_rows(x, mode, *, pre=None, temperature=1.0, power=1.0, eps=1e-6):
+    """Rows of `x` times r(|pre x|) (and pre): see include/iif_b200.h IIF_NORM_*."""
+    return _NormalizeRows.apply(x, pre, mode, temperature, power, eps)
+
+
 class _Linear(torch.autograd.Function):
     """Z = X W^T + b with the head's own GEMM kernels; `bf16` selects the tcgen05 path."""
 

@@ -287,9 +287,52 @@ class Linear(nn.Linear):
         return F_.linear(x, self.weight, self.bias, bf16=False)
 
 
+class NormedLinear(Linear):
+    """`LINEAR_LAYERS['NormedLinear']` (utils/normed_predictor.py:11-40):
+    z = F.linear(T x / (|x|^p + eps), w / (|w|^p + eps), bias) -- the operand normalisations and their
+    backward run in the library's row kernels, the contraction in the head's GEMMs.  Same constructor
+    (including the reference's spelling `tempearture`), same parameter names / init."""
+
+    def __init__(self, *args, tempearture=20, power=1.0, eps=1e-6, compute="bf16", **kwargs):
+        super().__init__(*args, compute=compute, **kwargs)
+        self.tempearture, self.power, self.eps = tempearture, power, eps
+        self.init_weights()
+
+    def init_weights(self):
+        nn.init.normal_(self.weight, mean=0, std=0.01)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, 0)
+
+    def _class_scale(self):
+        return None
+
+    def forward(self, x):
+        from . import _lib
+        w_ = F_.normalize_rows(self.weight, _lib.NORM_NORMED, pre=self._class_scale(), temperature=1.0,
+                               power=self.power, eps=self.eps)
+        x_ = F_.normalize_rows(x, _lib.NORM_NORMED, temperature=self.tempearture, power=self.power, eps=self.eps)
+        return F_.linear(x_, w_, self.bias, bf16=(self.compute == "bf16"))
+
+
+class IIFNormedLinear(NormedLinear):
+    """`LINEAR_LAYERS['IIFNormedLinear']` (utils/normed_predictor.py:43-76): NormedLinear on the class rows
+    pre-multiplied by their IIF weight, w' = iif_c w_c (CSV column `variant`, background entry 1.0)."""
+
+    def __init__(self, *args, tempearture=20, power=1.0, eps=1e-6, path="./lvis_files/idf_1204.csv",
+                 variant="base2_obj", compute="bf16", device="cuda", **kwargs):
+        super().__init__(*args, tempearture=tempearture, power=power, eps=eps, compute=compute, **kwargs)
+        import pandas as pd
+        vals = pd.read_csv(path)[variant].values.tolist()        # KeyError on an unknown column, as the reference
+        vals = vals[1:] + [1.0]                                    # drop the placeholder row, +1 for background
+        self.iif_weights = torch.tensor(vals, device=device, dtype=torch.float).unsqueeze(1)
+
+    def _class_scale(self):
+        return self.iif_weights.reshape(-1)
+
+
 def register_all():
-    """Register into mmdet's registries (LOSSES: IIFLoss, FasaIIFLoss; LINEAR_LAYERS: Linear) when
-    mmdet is importable; returns the names registered."""
+    """Register into mmdet's registries (LOSSES: IIFLoss, FasaIIFLoss; LINEAR_LAYERS: Linear, NormedLinear,
+    IIFNormedLinear) when mmdet is importable; returns the names registered."""
     done = []
     try:
         from mmdet.models.builder import LOSSES  # type: ignore
@@ -297,8 +340,9 @@ def register_all():
             LOSSES.register_module(name=cls.__name__, force=True, module=cls)
             done.append(cls.__name__)
         from mmdet.models.utils.builder import LINEAR_LAYERS  # type: ignore
-        LINEAR_LAYERS.register_module(name="Linear", force=True, module=Linear)
-        done.append("Linear")
+        for cls in (Linear, NormedLinear, IIFNormedLinear):
+            LINEAR_LAYERS.register_module(name=cls.__name__, force=True, module=cls)
+            done.append(cls.__name__)
     except ImportError:
         pass
     return done

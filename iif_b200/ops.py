@@ -254,6 +254,50 @@ def scale_rows(x, g=None, *, bf16=False, pad_ld=False):
     return out if ldo == cols else out[:, :cols]
 
 
+def row_scale_from_norm(x, mode, *, pre=None, temperature=1.0, power=1.0, eps=1e-6, want_c=True):
+    """(a, c): per-row operand multiplier a_i = pre_i r(|pre_i x_i|) and backward coefficient c_i (see the header)."""
+    x = _rows(x, "x", torch.float32)
+    rows, cols = x.shape
+    dev = x.device
+    pre = _vec(pre, "pre", rows)
+    a = torch.empty(rows, dtype=torch.float32, device=dev)
+    c = torch.empty(rows, dtype=torch.float32, device=dev) if want_c else None
+    if rows:
+        _lib.check(_lib.load().iif_row_scale_from_norm(_ptr(x), _ld(x), rows, cols, _ptr(pre), int(mode), float(temperature),
+                                                       float(power), float(eps), _ptr(a), _ptr(c), None, _stream(dev)),
+                   "row_scale_from_norm")
+    return a, c
+
+
+def row_dot(u, v):
+    u = _rows(u, "u", torch.float32)
+    v = _rows(v, "v", torch.float32)
+    if u.shape != v.shape:
+        raise ValueError("row_dot: shape mismatch")
+    out = torch.empty(u.shape[0], dtype=torch.float32, device=u.device)
+    if u.shape[0]:
+        _lib.check(_lib.load().iif_row_dot(_ptr(u), _ld(u), _ptr(v), _ld(v), u.shape[0], u.shape[1], _ptr(out),
+                                           _stream(u.device)), "row_dot")
+    return out
+
+
+def rows_axpby(u, a=None, v=None, b=None, b2=None):
+    """out_i = a_i u_i + (b_i b2_i) v_i  (fp32)."""
+    u = _rows(u, "u", torch.float32)
+    rows, cols = u.shape
+    dev = u.device
+    if v is not None:
+        v = _rows(v, "v", torch.float32)
+        if v.shape != u.shape:
+            raise ValueError("rows_axpby: shape mismatch")
+    a, b, b2 = _vec(a, "a", rows), _vec(b, "b", rows), _vec(b2, "b2", rows)
+    out = torch.empty(rows, cols, dtype=torch.float32, device=dev)
+    if rows and cols:
+        _lib.check(_lib.load().iif_rows_axpby(_ptr(u), _ld(u), _ptr(a), _ptr(v), 0 if v is None else _ld(v), _ptr(b),
+                                              _ptr(b2), rows, cols, _ptr(out), cols, _stream(dev)), "rows_axpby")
+    return out
+
+
 def colsum(dz, alpha=None):
     _cuda(dz, "dz")
     rows, cols = dz.shape

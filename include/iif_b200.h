@@ -55,6 +55,13 @@ enum {
 
 enum { IIF_DTYPE_F32 = 0, IIF_DTYPE_BF16 = 1 };
 
+/* Row-norm -> operand multiplier of the normalised classifiers (see iif_row_scale_from_norm). */
+enum {
+  IIF_NORM_NORMED = 0, /* T / (n^p + eps): mmdet NormedLinear / IIFNormedLinear, normed_predictor.py:36-40,70-76 */
+  IIF_NORM_COS = 1,    /* T / (1 + n):     CosNorm_Classifier features, cls/resnet_cifar.py:67-69              */
+  IIF_NORM_UNIT = 2    /* T / max(n, eps): unit rows (CosNorm weights :71, F.normalize)                        */
+};
+
 IIF_API int iif_abi_version(void);
 IIF_API const char* iif_error_string(int code);
 /* Number of kernels this library has launched since load (all streams); bench.py's gpu_launches. */
@@ -180,6 +187,25 @@ IIF_API int iif_scale_rows(const float* in, int64_t ldi, const float* g, int64_t
  * The bias gradient of AddmmBackward (a10). */
 IIF_API int iif_colsum(const void* dz, int dz_dtype, int64_t lddz, const float* alpha_dev, int64_t rows,
                int64_t cols, float* db, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * normalised classifiers: the reference normalises the OPERANDS of fc_cls and then calls
+ * F.linear (seg/mmdet/models/utils/normed_predictor.py:36-40,70-76; cls/resnet_cifar.py:66-77); so does
+ * this path, with three row kernels around the head's GEMMs.  All fp32, rows with any leading dimension.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Per row i: n = | pre_i x_i |_2 (pre optional: the IIF weight of a class row), r = r_mode(n; T, p, eps):
+ *   a[i] = pre_i r(n)                 (y_i = a[i] x_i is the normalised operand row)
+ *   c[i] = pre_i^3 r'(n) / n          (optional; backward: dx_i = a[i] g_i + c[i] (x_i . g_i) x_i)
+ *   norm[i] = n                       (optional) */
+IIF_API int iif_row_scale_from_norm(const float* x, int64_t ldx, int64_t rows, int64_t cols, const float* pre, int mode,
+                            float temperature, float power, float eps, float* a, float* c, float* norm, void* stream);
+/* out[i] = u_i . v_i */
+IIF_API int iif_row_dot(const float* u, int64_t ldu, const float* v, int64_t ldv, int64_t rows, int64_t cols, float* out,
+                void* stream);
+/* out_i = a[i] u_i + (b[i] b2[i]) v_i   (a, b, b2 optional = 1; v == NULL drops the second term) */
+IIF_API int iif_rows_axpby(const float* u, int64_t ldu, const float* a, const float* v, int64_t ldv, const float* b,
+                   const float* b2, int64_t rows, int64_t cols, float* out, int64_t ldo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a)/(c) fc_cls GEMMs.  *_bf16: tcgen05.mma (TMEM accumulators, TMA-fed), bf16 operands, fp32

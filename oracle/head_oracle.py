@@ -273,6 +273,56 @@ def focal_cls(z, label, gamma, alpha=None, weights=None):
 
 
 # ----------------------------------------------------------------------------------------
+# 8f-1  normalised classifiers
+# ----------------------------------------------------------------------------------------
+def _norm_rows(x, pre, mode, T, p, eps):
+    """y_i = pre_i r(n_i) x_i with n_i = |pre_i x_i|; returns (y, a, c) with the backward
+    dx_i = a_i g_i + c_i (x_i . g_i) x_i."""
+    x = np.asarray(x, np.float64)
+    pre = np.ones(x.shape[0]) if pre is None else np.asarray(pre, np.float64).reshape(-1)
+    n = np.abs(pre) * np.sqrt((x * x).sum(1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if mode == "normed":      # T / (n^p + eps)
+            r = T / (n ** p + eps)
+            dr = np.where(n > 0, -T * p * n ** (p - 1.0) / (n ** p + eps) ** 2, 0.0)
+        elif mode == "cos":       # T / (1 + n)
+            r = T / (1.0 + n)
+            dr = -T / (1.0 + n) ** 2
+        else:                     # T / n
+            r = T / np.maximum(n, eps)
+            dr = np.where(n > eps, -T / n ** 2, 0.0)
+        c = np.where(n > 0, pre ** 3 * dr / n, 0.0)
+    a = pre * r
+    return a[:, None] * x, a, c
+
+
+def _norm_rows_bwd(x, g, a, c):
+    x = np.asarray(x, np.float64)
+    return a[:, None] * g + (c * (x * g).sum(1))[:, None] * x
+
+
+def normed_linear(x, w, b, gz, temperature=20.0, power=1.0, eps=1e-6, iif=None):
+    """mmdet NormedLinear / IIFNormedLinear forward and backward (utils/normed_predictor.py:36-40, 70-76):
+    z = F.linear(T x/(|x|^p+eps), w'/(|w'|^p+eps), b), w' = iif_c w_c.  Returns z, dx, dw, db for upstream gz."""
+    x_, ax, cx = _norm_rows(x, None, "normed", temperature, power, eps)
+    w_, aw, cw = _norm_rows(w, iif, "normed", 1.0, power, eps)
+    z = x_ @ w_.T + (0.0 if b is None else np.asarray(b, np.float64)[None, :])
+    gz = np.asarray(gz, np.float64)
+    dx = _norm_rows_bwd(x, gz @ w_, ax, cx)
+    dw = _norm_rows_bwd(w, gz.T @ x_, aw, cw)
+    return z, dx, dw, gz.sum(0)
+
+
+def cosnorm_classifier(x, w, gz, scale=16.0):
+    """CosNorm_Classifier (cls/resnet_cifar.py:66-77): z = (scale x/(1+|x|)) (w/|w|)^T.  Returns z, dx, dw."""
+    ex, ax, cx = _norm_rows(x, None, "cos", scale, 1.0, 0.0)
+    ew, aw, cw = _norm_rows(w, None, "unit", 1.0, 1.0, 0.0)
+    z = ex @ ew.T
+    gz = np.asarray(gz, np.float64)
+    return z, _norm_rows_bwd(x, gz @ ew, ax, cx), _norm_rows_bwd(w, gz.T @ ex, aw, cw)
+
+
+# ----------------------------------------------------------------------------------------
 # a9  accuracy
 # ----------------------------------------------------------------------------------------
 def label_rank(z, label):

@@ -72,6 +72,44 @@ def load_mmdet_losses():
     return types.SimpleNamespace(**out)
 
 
+def load_normed_predictors():
+    """mmdet/models/utils/normed_predictor.py behind stub registries (mmcv.cnn.CONV_LAYERS, .builder.LINEAR_LAYERS)."""
+    name = "mmdet.models.utils.normed_predictor"
+    if name in sys.modules:
+        return sys.modules[name]
+    load_mmdet_losses()
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda c: c
+
+    cnn = types.ModuleType("mmcv.cnn")
+    cnn.CONV_LAYERS = _Reg()
+    sys.modules["mmcv.cnn"] = cnn
+    sys.modules["mmcv"].cnn = cnn
+    pkg = types.ModuleType("mmdet.models.utils")
+    pkg.__path__ = []
+    sys.modules.setdefault("mmdet.models.utils", pkg)
+    b = types.ModuleType("mmdet.models.utils.builder")
+    b.LINEAR_LAYERS = _Reg()
+    sys.modules["mmdet.models.utils.builder"] = b
+    spec = importlib.util.spec_from_file_location(
+        name, os.path.join(REF, "instance_segmentation", "mmdet", "models", "utils", "normed_predictor.py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def load_resnet_cifar():
+    """classification/resnet_cifar.py (CosNorm_Classifier); its constructor calls .cuda(): use cpu_shims()."""
+    p = os.path.join(REF, "classification")
+    if p not in sys.path:
+        sys.path.insert(0, p)
+    import resnet_cifar  # noqa: the reference module
+    return resnet_cifar
+
+
 @contextlib.contextmanager
 def cpu_shims():
     """Run reference code that names CUDA on a CPU-only host (device remap only)."""

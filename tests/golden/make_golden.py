@@ -169,6 +169,43 @@ def gen_cls_focal():
     print("cls_focal.npz", len(out), "arrays")
 
 
+# ------------------------------------------------------------------ normalised classifiers
+def gen_normed():
+    """mmdet NormedLinear / IIFNormedLinear (utils/normed_predictor.py) and cls CosNorm_Classifier
+    (resnet_cifar.py:50-78), unmodified, in float64: forward and the gradients of x, weight, bias for a
+    random upstream gradient."""
+    g = torch.Generator().manual_seed(5)
+    out = {}
+    with ref_loader.cpu_shims():
+        npred = ref_loader.load_normed_predictors()
+        rc = ref_loader.load_resnet_cifar()
+
+        def run(tag, mod, B, D):
+            mod = mod.double()
+            with torch.no_grad():
+                mod.weight.copy_(torch.randn(mod.weight.shape, generator=g, dtype=torch.float64) * 0.1)
+                if getattr(mod, "bias", None) is not None:
+                    mod.bias.copy_(torch.randn(mod.bias.shape, generator=g, dtype=torch.float64) * 0.1)
+            x = (torch.randn(B, D, generator=g, dtype=torch.float64) * 1.5).requires_grad_(True)
+            z = mod(x)
+            gz = torch.randn(z.shape, generator=g, dtype=torch.float64)
+            z.backward(gz)
+            out[f"{tag}_x"], out[f"{tag}_w"], out[f"{tag}_gz"], out[f"{tag}_z"] = npy(x), npy(mod.weight), npy(gz), npy(z)
+            out[f"{tag}_dx"], out[f"{tag}_dw"] = npy(x.grad), npy(mod.weight.grad)
+            if getattr(mod, "bias", None) is not None:
+                out[f"{tag}_b"], out[f"{tag}_db"] = npy(mod.bias), npy(mod.bias.grad)
+
+        run("normed_p1", npred.NormedLinear(64, 36), 24, 64)
+        run("normed_p2", npred.NormedLinear(64, 36, tempearture=10, power=2.0, eps=1e-3), 24, 64)
+        run("normed_nobias", npred.NormedLinear(64, 36, bias=False), 24, 64)
+        iifm = npred.IIFNormedLinear(32, 1204, path=ref_loader.csv_path("idf_1204.csv"), variant="base2_obj")
+        out["iifnormed_iif"] = npy(iifm.iif_weights.reshape(-1))
+        run("iifnormed", iifm, 16, 32)
+        run("cosnorm", rc.CosNorm_Classifier(64, 36, scale=16), 24, 64)
+    np.savez_compressed(os.path.join(HERE, "normed.npz"), **out)
+    print("normed.npz", len(out), "arrays")
+
+
 # ------------------------------------------------------------------ mmdet IIFLoss / FasaIIFLoss
 def gen_mmdet():
     g = torch.Generator().manual_seed(2)
@@ -287,6 +324,7 @@ if __name__ == "__main__":
     gen_cls_mixup()
     gen_cls_bce()
     gen_cls_focal()
+    gen_normed()
     gen_mmdet()
     gen_mmdet_bce()
     gen_tables()

@@ -396,3 +396,82 @@ def test_head_pipeline_host_batches():
     with pytest.raises(ValueError):
         pipe.submit(0, hx[0].float(), hy[0])
     pipe.close()
+
+
+# ------------------------------------------------------------------ normalised classifiers
+def _load(mod, g, tag):
+    with torch.no_grad():
+        mod.weight.copy_(T(g[f"{tag}_w"]).float())
+        if getattr(mod, "bias", None) is not None:
+            mod.bias.copy_(T(g[f"{tag}_b"]).float())
+
+
+def _check_normed(mod, g, tag, tol):
+    x = T(g[f"{tag}_x"]).float().requires_grad_(True)
+    z = mod(x)
+    z.backward(T(g[f"{tag}_gz"]).float())
+    assert rel_err(N(z), g[f"{tag}_z"]) < tol
+    assert rel_err(N(x.grad), g[f"{tag}_dx"]) < tol
+    assert rel_err(N(mod.weight.grad), g[f"{tag}_dw"]) < tol
+    if getattr(mod, "bias", None) is not None:
+        assert rel_err(N(mod.bias.grad), g[f"{tag}_db"]) < tol
+
+
+@pytest.mark.parametrize("compute,tol", [("fp32", 2e-5), ("bf16", TOL_BF16)])
+def test_normed_linear_modules_golden(golden, tmp_path, compute, tol):
+    """NormedLinear / IIFNormedLinear / CosNorm_Classifier against the unmodified reference modules
+    (tests/golden/normed.npz, float64): forward, dX, dW, db."""
+    from iif_b200.mmdet import NormedLinear, IIFNormedLinear
+    from iif_b200.classification import CosNorm_Classifier
+    g = golden("normed")
+    m = NormedLinear(64, 36, compute=compute).to(DEV)
+    assert isinstance(m, torch.nn.Linear) and m.tempearture == 20
+    _load(m, g, "normed_p1"); _check_normed(m, g, "normed_p1", tol)
+    m = NormedLinear(64, 36, tempearture=10, power=2.0, eps=1e-3, compute=compute).to(DEV)
+    _load(m, g, "normed_p2"); _check_normed(m, g, "normed_p2", tol)
+    m = NormedLinear(64, 36, bias=False, compute=compute).to(DEV)
+    _load(m, g, "normed_nobias"); _check_normed(m, g, "normed_nobias", tol)
+    # the CSV the module reads: placeholder row 0, then the per-class column; the module appends 1.0 for background
+    import pandas as pd
+    col = np.concatenate([[1.0], g["iifnormed_iif"][:-1]])
+    path = str(tmp_path / "idf.csv")
+    pd.DataFrame({"base2_obj": col}).to_csv(path, index=False)
+    m = IIFNormedLinear(32, 1204, path=path, variant="base2_obj", compute=compute, device=DEV).to(DEV)
+    assert np.array_equal(N(m.iif_weights).reshape(-1), g["iifnormed_iif"].astype(np.float32))
+    _load(m, g, "iifnormed"); _check_normed(m, g, "iifnormed", tol)
+    with pytest.raises(KeyError):
+        IIFNormedLinear(32, 1204, path=path, variant="log_adj", device=DEV)
+    c = CosNorm_Classifier(64, 36, scale=16, compute=compute, device=DEV)
+    _load(c, g, "cosnorm"); _check_normed(c, g, "cosnorm", tol)
+
+
+def test_normed_linear_head_shape_vs_oracle():
+    """LVIS-sized NormedLinear head (1024 RoIs x 1024-d x 1204 classes, bf16 GEMMs) vs the float64 oracle, and the
+    row kernels on ragged / unaligned rows."""
+    from iif_b200.mmdet import NormedLinear
+    from iif_b200 import ops, _lib
+    rng = np.random.default_rng(0)
+    B, D, C = 1024, 1024, 1204
+    x = np.maximum(rng.standard_normal((B, D)), 0).astype(np.float32)
+    w = (rng.standard_normal((C, D)) * 0.01).astype(np.float32)
+    b = (rng.standard_normal(C) * 0.01).astype(np.float32)
+    gz = (rng.standard_normal((B, C)) / B).astype(np.float32)
+    m = NormedLinear(D, C, compute="bf16").to(DEV)
+    with torch.no_grad():
+        m.weight.copy_(T(w)); m.bias.copy_(T(b))
+    xt = T(x).requires_grad_(True)
+    z = m(xt)
+    z.backward(T(gz))
+    zr, dxr, dwr, dbr = ho.normed_linear(x, w, b, gz)
+    assert rel_err(N(z), zr) < TOL_BF16 and rel_err(N(xt.grad), dxr) < TOL_BF16
+    assert rel_err(N(m.weight.grad), dwr) < TOL_BF16 and rel_err(N(m.bias.grad), dbr) < TOL_BF16
+    # row kernels alone, 7 x 13 (scalar path) with a zero row
+    u = rng.standard_normal((7, 13)).astype(np.float32); u[3] = 0
+    v = rng.standard_normal((7, 13)).astype(np.float32)
+    pre = rng.uniform(-2, 2, 7).astype(np.float32)
+    a, c = ops.row_scale_from_norm(T(u), _lib.NORM_NORMED, pre=T(pre), temperature=3.0, power=1.5, eps=1e-4)
+    _, ar, cr = ho._norm_rows(u, pre, "normed", 3.0, 1.5, 1e-4)
+    assert rel_err(N(a), ar) < 1e-5 and rel_err(N(c), cr) < 1e-5
+    assert rel_err(N(ops.row_dot(T(u), T(v))), (u.astype(np.float64) * v).sum(1)) < 1e-5
+    out = ops.rows_axpby(T(u), T(pre), T(v), T(pre), T(pre))
+    assert rel_err(N(out), pre[:, None] * u + (pre * pre)[:, None] * v) < 1e-6

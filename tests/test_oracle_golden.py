@@ -302,3 +302,30 @@ def test_focal_golden(golden, gamma, alpha, red, wtag):
     key = f"{gamma}_{alpha}_{wtag}_{red}"
     close(loss.sum() * scale, g[f"loss_{key}"], rtol=3e-5)
     close(dz * scale, g[f"dz_{key}"], rtol=3e-5)
+
+
+# ------------------------------------------------------------------ normalised classifiers
+@pytest.mark.parametrize("tag,kw", [("normed_p1", dict(temperature=20.0, power=1.0, eps=1e-6)),
+                                    ("normed_p2", dict(temperature=10.0, power=2.0, eps=1e-3)),
+                                    ("normed_nobias", dict(temperature=20.0, power=1.0, eps=1e-6)),
+                                    ("iifnormed", dict(temperature=20.0, power=1.0, eps=1e-6))])
+def test_normed_linear_golden(golden, tag, kw):
+    """mmdet NormedLinear / IIFNormedLinear (unmodified reference, float64) vs ho.normed_linear."""
+    g = golden("normed")
+    iif = g["iifnormed_iif"] if tag == "iifnormed" else None
+    b = g[f"{tag}_b"] if f"{tag}_b" in g else None
+    z, dx, dw, db = ho.normed_linear(g[f"{tag}_x"], g[f"{tag}_w"], b, g[f"{tag}_gz"], iif=iif, **kw)
+    close(z, g[f"{tag}_z"], rtol=1e-9)
+    close(dx, g[f"{tag}_dx"], rtol=1e-9)
+    close(dw, g[f"{tag}_dw"], rtol=1e-9)
+    if b is not None:
+        close(db, g[f"{tag}_db"], rtol=1e-9)
+
+
+def test_cosnorm_golden(golden):
+    """cls CosNorm_Classifier (unmodified reference, float64) vs ho.cosnorm_classifier."""
+    g = golden("normed")
+    z, dx, dw = ho.cosnorm_classifier(g["cosnorm_x"], g["cosnorm_w"], g["cosnorm_gz"], scale=16.0)
+    close(z, g["cosnorm_z"], rtol=1e-9)
+    close(dx, g["cosnorm_dx"], rtol=1e-9)
+    close(dw, g["cosnorm_dw"], rtol=1e-9)
