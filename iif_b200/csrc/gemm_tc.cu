@@ -184,8 +184,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int split = local % P.splits;
   const int tile = local / P.splits;
   const int n0 = (tile % P.tiles_n) * BN, m0 = (tile / P.tiles_n) * TILE_M;
-  const int kb_begin = split * P.kb_per_split;
-  const int kb_end = min(P.kb_total, kb_begin + P.kb_per_split);
+  // K blocks of a split tile are dealt round-robin: at any moment the `splits` CTAs of a tile stream ADJACENT
+  // 128-byte chunks of the same operand rows (splits x 128 B contiguous per row) instead of chunks a quarter
+  // of a row apart -- friendlier to DRAM pages when the operands are cold.  Local index i -> block kb_of(i).
+  const int kb_begin = 0;
+  const int kb_end = (P.kb_total - split + P.splits - 1) / P.splits;          // blocks split, split+S, split+2S, ...
+  auto kb_of = [&](int i) { return split + i * P.splits; };
   const bool do_db = P.db_out != nullptr && n0 == 0;
 
   if (warp == 0 && lane == 0) {
@@ -258,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     bool b_issued = false;
     auto issue_b = [&]() {
       if (threadIdx.x == 0 && !b_issued)
-        for (int i = 0; i < n_first; ++i) load_b(i, kb_begin + i);
+        for (int i = 0; i < n_first; ++i) load_b(i, kb_of(i));
       b_issued = true;
     };
     for (int64_t r = blockIdx.x; r < g.loss.B; r += gridDim.x) {
@@ -288,8 +292,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (kb - kb_begin >= early_b) load_b(stage, kb);
-        load_a(stage, kb);
+        if (kb - kb_begin >= early_b) load_b(stage, kb_of(kb));
+        load_a(stage, kb_of(kb));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       stamp(g, 3);                       // all TMA loads issued
