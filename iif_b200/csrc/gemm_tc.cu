@@ -49,6 +49,7 @@
 
 #include <mutex>
 #include <unordered_map>
+#include <utility>
 
 #include "common.cuh"
 #include "loss_row.cuh"
@@ -88,6 +89,7 @@ struct TcProblem {
   int a_mn, b_mn;
   const float* alpha; const float* bias; const float* col_scale;
   void* out; int out_bf16; int64_t ldo; int epi_tma;
+  int ksplit_add;                                   // > 1: K split over CTAs that ADD their tiles into a zeroed output
   float* out2; int64_t ldo2;
   float4* partial;                                  // [tiles][splits][TILE_F4] fp32x4, layout part_idx()
   unsigned long long* counters;                     // [tiles] arrival epochs (see EPOCH_UNIT)
@@ -181,15 +183,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const CUtensorMap* tmB = pi ? &tmB1 : &tmB0;
   const CUtensorMap* tmO = pi ? &tmO1 : &tmO0;
   const int local = (int)blockIdx.x - g.cta_begin[pi];
-  const int split = local % P.splits;
-  const int tile = local / P.splits;
+  // K splits: either the rendezvous form (P.splits: partial tiles + in-kernel deterministic reduction) or, for
+  // long K with too many CTAs to be co-resident, the additive form (P.ksplit_add: TMA reduce-add into a zeroed
+  // fp32 output -- no rendezvous, summation order across splits not fixed)
+  const int ksp = P.ksplit_add > 1 ? P.ksplit_add : P.splits;
+  const int split = local % ksp;
+  const int tile = local / ksp;
   const int n0 = (tile % P.tiles_n) * BN, m0 = (tile / P.tiles_n) * TILE_M;
   // K blocks of a split tile are dealt round-robin: at any moment the `splits` CTAs of a tile stream ADJACENT
   // 128-byte chunks of the same operand rows (splits x 128 B contiguous per row) instead of chunks a quarter
   // of a row apart -- friendlier to DRAM pages when the operands are cold.  Local index i -> block kb_of(i).
   const int kb_begin = 0;
-  const int kb_end = (P.kb_total - split + P.splits - 1) / P.splits;          // blocks split, split+S, split+2S, ...
-  auto kb_of = [&](int i) { return split + i * P.splits; };
+  const int kb_end = (P.kb_total - split + ksp - 1) / ksp;                    // blocks split, split+S, split+2S, ...
+  auto kb_of = [&](int i) { return split + i * ksp; };
   const bool do_db = P.db_out != nullptr && n0 == 0;
 
   if (warp == 0 && lane == 0) {
@@ -332,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // epilogue vectors of this tile's 128 columns (read after the dependency wait: parameters)
     for (int i = lane; i < BN; i += 32) {
       const int n = n0 + i;
-      s_bias[i] = (P.bias && n < P.N) ? __ldg(P.bias + n) : 0.f;
+      s_bias[i] = (P.bias && n < P.N && !(P.ksplit_add > 1 && split != 0)) ? __ldg(P.bias + n) : 0.f;
       s_scale[i] = (P.col_scale && n < P.N) ? __ldg(P.col_scale + n) : 0.f;
     }
   }
@@ -386,7 +392,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) {
         const int mr = m0 + q * 32, nc = n0 + h * 64;
         if (mr < P.M) {
-          if (P.out_bf16) {
+          if (P.ksplit_add > 1) {                       // fp32 only (host guarantees)
+            if (nc < P.N) ptx::tma_reduce_add_2d(tmO, wbase, nc, mr);
+            if (nc + 32 < P.N) ptx::tma_reduce_add_2d(tmO, wbase + 4096u, nc + 32, mr);
+          } else if (P.out_bf16) {
             if (nc < P.N) ptx::tma_store_2d(tmO, wbase, nc, mr);
           } else {
             if (nc < P.N) ptx::tma_store_2d(tmO, wbase, nc, mr);
@@ -427,7 +436,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (do_db && h == 0) {                   // db of this row: first of the 16 equal columns
       const uint32_t v = ptx::tmem_ld1(tmem_base + ((uint32_t)(q * 32) << 16) + BN);
       ptx::tmem_ld_wait();
-      if (m0 + row < P.M) P.db_out[m0 + row] = __uint_as_float(v) * alpha;
+      if (m0 + row < P.M) {
+        if (P.ksplit_add > 1) atomicAdd(P.db_out + m0 + row, __uint_as_float(v) * alpha);
+        else P.db_out[m0 + row] = __uint_as_float(v) * alpha;
+      }
     }
   } else {
     // ---- split-K: partial tile -> L2 workspace, meet at the tile's counter, reduce 1/splits of the rows
@@ -633,6 +645,8 @@ static int resident_capacity(int* detail = nullptr) {
 
 struct Plan {
   int tiles_m, tiles_n, kb_total, kb_per_split, splits;
+  int ksplit_add = 1;
+  int ctas() const { return tiles_m * tiles_n * (ksplit_add > 1 ? ksplit_add : splits); }
   size_t partial_bytes() const { return splits > 1 ? (size_t)tiles_m * tiles_n * splits * TILE_M * BN * 4 : 0; }
   size_t db_bytes() const { return splits > 1 ? (size_t)tiles_m * splits * TILE_M * 4 : 0; }   // 512-byte multiples
 };
@@ -691,11 +705,13 @@ static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, unsign
   P->M = (int)d.M; P->N = (int)d.N; P->K = (int)d.K;
   P->tiles_m = p.tiles_m; P->tiles_n = p.tiles_n; P->kb_total = p.kb_total; P->kb_per_split = p.kb_per_split;
   P->splits = p.splits; P->a_mn = d.a_mn; P->b_mn = d.b_mn;
+  P->ksplit_add = p.ksplit_add;
   P->alpha = d.alpha; P->bias = d.bias; P->col_scale = d.col_scale;
   P->out = d.out; P->out_bf16 = d.out_bf16; P->ldo = d.ldo;
   P->out2 = d.out2; P->ldo2 = d.ldo2;
   // TMA store: one output, 16-byte aligned base and row pitch
   P->epi_tma = p.splits == 1 && d.out && !d.out2 && aligned16(d.out) && (d.ldo * (d.out_bf16 ? 2 : 4)) % 16 == 0;
+  if (p.ksplit_add > 1 && !P->epi_tma) return IIF_EINVAL;   // (the planner only picks it for TMA-addressable fp32 outputs)
   if (P->epi_tma) {
     rc = make_map(mo, d.out, !d.out_bf16, (uint64_t)d.N, (uint64_t)d.M, (uint64_t)d.ldo, d.out_bf16 ? 64 : 32, 32);
     if (rc) return rc;
@@ -712,8 +728,10 @@ static long long* g_dbg = nullptr;   // iif_debug_timing
 static std::atomic<int> g_reserved_slots{0};   // iif_gemm_reserve_slots
 
 // Launch one or two problems in one grid.
-static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes, cudaStream_t st,
+static int launch_group(const GemmDesc* d_in, int nprob, void* ws, size_t ws_bytes, cudaStream_t st,
                         const RowArgs* loss = nullptr, bool dry_run = false) {
+  GemmDesc d[2];
+  for (int i = 0; i < nprob; ++i) d[i] = d_in[i];
   int cap = resident_capacity();
   if (cap <= 0) { cudaGetLastError(); return IIF_EDRIVER; }
   // resident-CTA slots promised to kernels that overlap these launches AND block on other GPUs (the
@@ -746,6 +764,31 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
         for (int i = 0; i < 2; ++i) { plans[i].splits = 1; plans[i].kb_per_split = plans[i].kb_total; }
     }
   }
+  // Long K, few tiles, grid too large for the rendezvous (e.g. dW of a 64k-row batch: 128 tiles x 1024 k-blocks
+  // next to 8192 dX tiles): split K over CTAs that reduce-add into the zeroed fp32 output through the TMA unit.
+  for (int i = 0; i < nprob && !dry_run && !loss; ++i) {
+    const int tiles = plans[i].tiles_m * plans[i].tiles_n;
+    const bool tma_ok = d[i].out && !d[i].out_bf16 && !d[i].out2 && aligned16(d[i].out) && (d[i].ldo * 4) % 16 == 0;
+    if (plans[i].splits == 1 && tma_ok && plans[i].kb_total >= 64 && tiles < 4 * kNumSMs) {
+      int s = (4 * kNumSMs + tiles - 1) / tiles;
+      if (s > plans[i].kb_total / 16) s = plans[i].kb_total / 16;
+      if (s > 32) s = 32;
+      if (s > 1) {
+        plans[i].ksplit_add = s;
+        cudaError_t e = cudaMemset2DAsync(d[i].out, (size_t)d[i].ldo * 4, 0, (size_t)d[i].N * 4, (size_t)d[i].M, st);
+        if (e == cudaSuccess && d[i].db_out) e = cudaMemsetAsync(d[i].db_out, 0, (size_t)d[i].M * 4, st);
+        if (e != cudaSuccess) return (int)e;
+      }
+    }
+  }
+  // CTAs are dispatched in block order: the problem with the longer K loop per CTA goes first (no long tail)
+  if (nprob == 2) {
+    auto per_cta = [&](int i) {
+      const int ksp = plans[i].ksplit_add > 1 ? plans[i].ksplit_add : plans[i].splits;
+      return (plans[i].kb_total + ksp - 1) / ksp;
+    };
+    if (per_cta(1) > per_cta(0)) { std::swap(d[0], d[1]); std::swap(plans[0], plans[1]); }
+  }
   size_t need = 0;
   bool any_split = false;
   for (int i = 0; i < nprob; ++i) {
@@ -769,7 +812,7 @@ static int launch_group(const GemmDesc* d, int nprob, void* ws, size_t ws_bytes,
     int rc = fill_problem(d[i], plans[i], partial, counters, dbp, &g.p[i], &maps[2 * i], &maps[2 * i + 1], &maps[4 + i]);
     if (rc) return rc;
     g.cta_begin[i] = cta;
-    cta += plans[i].tiles_m * plans[i].tiles_n * plans[i].splits;
+    cta += plans[i].ctas();
   }
   g.cta_begin[nprob] = cta;
   g.nprob = nprob;

@@ -127,3 +127,25 @@ def test_gemm_bf16_linearity_full_size(ops):
     idx = torch.randint(0, B, (64,), device=DEV)
     ref = ho.linear_fwd(N(x1[idx]), N(w))
     assert rel_err(N(z1[idx]), ref) < 2e-5
+
+
+def test_linear_bwd_long_k_additive_split(ops):
+    """Big batch: dW = dZ^T X has few tiles and a very long K (= B).  Its K is split over CTAs that reduce-add
+    into the zeroed output through the TMA unit (no rendezvous: the grid is far larger than the resident
+    capacity), next to thousands of dX tiles in the same launch; db through fp32 atomics."""
+    B, D, C = 16384, 512, 1000
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (C, D)) / np.sqrt(D)).astype(np.float32)
+    dz = (rng.standard_normal((B, C)) / B).astype(np.float32)
+    xb, wb, dzb = bf16_round(x), bf16_round(w), bf16_round(dz)
+    bf = torch.bfloat16
+    dzt = ops.scale_rows(T(dz), None, bf16=True, pad_ld=True)
+    dxr, dwr, dbr = ho.linear_bwd(dzb, xb, wb)
+    for _ in range(2):                                    # the output is re-zeroed by every call
+        dx, dw, db = ops.linear_bwd(dzt, T(x, bf), T(w, bf))
+    assert rel_err(N(dx), dxr) < 2e-5
+    assert rel_err(N(dw), dwr) < 2e-5
+    assert rel_err(N(db), dbr) < 2e-5
+    dw2 = ops.linear_bwd_dw(dzt, T(x, bf), alpha=T(np.float32(0.5)))
+    assert rel_err(N(dw2), 0.5 * dwr) < 2e-5
