@@ -74,6 +74,9 @@ SIGNATURES = {
     "iif_pipeline_submit_device": (_i32, [_p, _i32]),
     "iif_pipeline_set_allreduce": (_i32, [_p, _p, _p, _p, _i32, _i32, C.POINTER(_i64), _i64, _i32, _i32, _i32]),
     "iif_pipeline_get_streams": (_i32, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
+    "iif_pipeline_enable_staged": (_i32, [_p]),
+    "iif_pipeline_staging": (_i32, [_p, _i32, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
+    "iif_pipeline_submit_staged": (_i32, [_p, _i32]),
     "iif_pipeline_wait": (_i32, [_p, _i32]),
     "iif_pipeline_stream_wait_step": (_i32, [_p, _i32, _p]),
     "iif_pipeline_hold_slot": (_i32, [_p, _i32, _p]),

@@ -836,6 +836,7 @@ static int launch_group(const GemmDesc* d_in, int nprob, void* ws, size_t ws_byt
   if (nprob == 1) { maps[2] = maps[0]; maps[3] = maps[1]; maps[5] = maps[4]; }
 
   if (dry_run) return IIF_OK;
+  const int variant = !g.fuse_loss ? 0 : (g.loss_ne == 4 ? 1 : (g.loss_ne == 8 ? 2 : 3));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)cta);
   cfg.blockDim = dim3(256);
@@ -847,7 +848,6 @@ static int launch_group(const GemmDesc* d_in, int nprob, void* ws, size_t ws_byt
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
   void* kargs[7] = {&maps[0], &maps[1], &maps[2], &maps[3], &maps[4], &maps[5], &g};
-  const int variant = !g.fuse_loss ? 0 : (g.loss_ne == 4 ? 1 : (g.loss_ne == 8 ? 2 : 3));
   cudaError_t e = cudaLaunchKernelExC(&cfg, kernel_variant(variant), kargs);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return (int)e;

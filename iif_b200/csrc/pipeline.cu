@@ -6,6 +6,8 @@
 // so step i+1's 1 MB feature copy hides under step i's kernels.  All GEMM launches stay on ONE compute
 // stream: the split-K rendezvous of gemm_tc.cu needs a grid to itself (two such grids running
 // concurrently could starve each other of resident-CTA slots), and one workspace serves every slot.
+#include <string.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -16,10 +18,16 @@ struct iif_pipeline {
     cudaEvent_t h2d_done, step_done, loss_done, release;
     bool used, held;
     int64_t ar_offset;
+    // staged mode (iif_pipeline_enable_staged): library-owned pinned host staging + one CUDA graph per slot
+    void* host_x; int64_t* host_y; float* host_loss;   // pinned; host_loss is mapped (the kernel stores into it)
+    iif_head_args a_staged;                            // = a, with loss_sum pointing at the mapped host_loss
+    cudaGraphExec_t exec;
+    int launches;                                      // kernel launches inside the slot's graph
   };
   int nslots;
   cudaStream_t s_h2d, s_compute, s_d2h, s_comm[4];
   int ar_lanes, ar_next;
+  bool staged; int primed;               // slot whose inputs are already on the device (prefetched), or -1
   Slot* slots;
   // optional data-parallel exchange after every step (iif_pipeline_set_allreduce)
   bool ar_on;
@@ -133,6 +141,102 @@ extern "C" int iif_pipeline_get_streams(iif_pipeline* p, void** h2d, void** comp
   return IIF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Staged mode: ONE driver call per step.  Every slot owns pinned host staging buffers (the data loader
+// writes the next batch there) and a CUDA graph captured from two streams:
+//     branch A (compute): forward launch -> loss + backward launch     of THIS slot
+//     branch B (copy)   : H2D of the NEXT slot's features + labels      (prefetch distance 1)
+// so the next batch's PCIe copy hides under this step's kernels without any per-step event traffic, and
+// the loss reaches the host through the kernel's own 4-byte store into mapped pinned memory.  Graph
+// launches are stream-ordered on the compute stream: steps never overlap each other (the split-K /
+// grid-barrier rendezvous of the GEMM launches needs that).  The un-graphed submit path costs ~11
+// driver calls per step, which on a slow or shared host is longer than the 30 us step itself.
+// ---------------------------------------------------------------------------------------------------
+static int copy_in(iif_pipeline* p, iif_pipeline::Slot& s, cudaStream_t st) {
+  const iif_head_args& a = s.a;
+  if (a.ldx == a.D)
+    IIF_CU(cudaMemcpyAsync(const_cast<void*>(a.x), s.host_x, (size_t)a.B * a.D * 2, cudaMemcpyHostToDevice, st));
+  else
+    IIF_CU(cudaMemcpy2DAsync(const_cast<void*>(a.x), (size_t)a.ldx * 2, s.host_x, (size_t)a.D * 2, (size_t)a.D * 2, a.B,
+                             cudaMemcpyHostToDevice, st));
+  IIF_CU(cudaMemcpyAsync(const_cast<int64_t*>(a.label), s.host_y, (size_t)a.B * 8, cudaMemcpyHostToDevice, st));
+  (void)p;
+  return IIF_OK;
+}
+
+extern "C" int iif_pipeline_enable_staged(iif_pipeline* p) {
+  if (!p || p->ar_on) return IIF_EINVAL;               // (data-parallel runs use the event-driven path)
+  if (p->staged) return IIF_OK;
+  cudaEvent_t fork, join;
+  IIF_CU(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  IIF_CU(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+  for (int i = 0; i < p->nslots; ++i) {
+    iif_pipeline::Slot& s = p->slots[i];
+    IIF_CU(cudaHostAlloc(&s.host_x, (size_t)s.a.B * s.a.D * 2, cudaHostAllocDefault));
+    IIF_CU(cudaHostAlloc(reinterpret_cast<void**>(&s.host_y), (size_t)s.a.B * 8, cudaHostAllocDefault));
+    IIF_CU(cudaHostAlloc(reinterpret_cast<void**>(&s.host_loss), 64, cudaHostAllocMapped));
+    memset(s.host_x, 0, (size_t)s.a.B * s.a.D * 2);
+    memset(s.host_y, 0, (size_t)s.a.B * 8);
+    *s.host_loss = 0.f;
+    float* dev_loss = nullptr;
+    IIF_CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_loss), s.host_loss, 0));
+    s.a_staged = s.a;
+    s.a_staged.loss_sum = dev_loss;
+    s.launches = iif_head_launches(&s.a_staged);
+    if (s.launches < 0) return s.launches;
+  }
+  // warm every slot once outside capture (function attributes, tensor-map cache), then capture
+  for (int i = 0; i < p->nslots; ++i) {
+    if (int rc = copy_in(p, p->slots[i], p->s_compute)) return rc;
+    if (int rc = iif_head_fwd_bwd_bf16(&p->slots[i].a_staged, p->s_compute)) return rc;
+  }
+  IIF_CU(cudaStreamSynchronize(p->s_compute));
+  for (int i = 0; i < p->nslots; ++i) {
+    iif_pipeline::Slot& s = p->slots[i];
+    iif_pipeline::Slot& nxt = p->slots[(i + 1) % p->nslots];
+    cudaGraph_t graph = nullptr;
+    IIF_CU(cudaStreamBeginCapture(p->s_compute, cudaStreamCaptureModeRelaxed));
+    IIF_CU(cudaEventRecord(fork, p->s_compute));
+    IIF_CU(cudaStreamWaitEvent(p->s_h2d, fork, 0));
+    int rc = copy_in(p, nxt, p->s_h2d);                               // branch B: prefetch the next slot's batch
+    if (!rc) rc = cudaEventRecord(join, p->s_h2d) == cudaSuccess ? IIF_OK : IIF_EDRIVER;
+    if (!rc) rc = iif_head_fwd_bwd_bf16(&s.a_staged, p->s_compute);   // branch A: this slot's step
+    if (!rc) rc = cudaStreamWaitEvent(p->s_compute, join, 0) == cudaSuccess ? IIF_OK : IIF_EDRIVER;
+    cudaError_t e = cudaStreamEndCapture(p->s_compute, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    IIF_CU(e);
+    IIF_CU(cudaGraphInstantiate(&s.exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  cudaEventDestroy(fork);
+  cudaEventDestroy(join);
+  p->staged = true;
+  p->primed = -1;
+  return IIF_OK;
+}
+
+extern "C" int iif_pipeline_staging(iif_pipeline* p, int slot, void** host_x, int64_t** host_label, float** host_loss) {
+  if (!p || !p->staged || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  if (host_x) *host_x = p->slots[slot].host_x;
+  if (host_label) *host_label = p->slots[slot].host_y;
+  if (host_loss) *host_loss = p->slots[slot].host_loss;
+  return IIF_OK;
+}
+
+extern "C" int iif_pipeline_submit_staged(iif_pipeline* p, int slot) {
+  if (!p || !p->staged || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  iif_pipeline::Slot& s = p->slots[slot];
+  if (p->primed != slot) {                              // first step, or the slots are not walked in order
+    if (int rc = copy_in(p, s, p->s_compute)) return rc;
+  }
+  IIF_CU(cudaGraphLaunch(s.exec, p->s_compute));
+  IIF_CU(cudaEventRecord(s.loss_done, p->s_compute));
+  iif::g_launches.fetch_add((uint64_t)s.launches, std::memory_order_relaxed);
+  p->primed = (slot + 1) % p->nslots;
+  s.used = true;
+  return IIF_OK;
+}
+
 extern "C" int iif_pipeline_wait(iif_pipeline* p, int slot) {
   if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
   if (!p->slots[slot].used) return IIF_OK;
@@ -166,6 +270,12 @@ extern "C" void iif_pipeline_destroy(iif_pipeline* p) {
   if (!p) return;
   iif_pipeline_sync(p);
   for (int i = 0; i < p->nslots; ++i) {
+    if (p->staged) {
+      if (p->slots[i].exec) cudaGraphExecDestroy(p->slots[i].exec);
+      cudaFreeHost(p->slots[i].host_x);
+      cudaFreeHost(p->slots[i].host_y);
+      cudaFreeHost(p->slots[i].host_loss);
+    }
     cudaEventDestroy(p->slots[i].h2d_done);
     cudaEventDestroy(p->slots[i].step_done);
     cudaEventDestroy(p->slots[i].loss_done);

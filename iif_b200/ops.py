@@ -571,6 +571,7 @@ class HeadPipeline:
         _lib.check(self._lib.iif_pipeline_create(C.byref(self._h), arr, n), "pipeline_create")
         self.host_loss = torch.zeros(n, dtype=torch.float32).pin_memory()
         self._loss_ptr = self.host_loss.data_ptr()
+        self._staged_last = [False] * n        # which mode produced each slot's latest loss
 
     def submit(self, slot: int, host_x: torch.Tensor, host_label: torch.Tensor) -> None:
         hs = self.steps[slot]
@@ -584,6 +585,7 @@ class HeadPipeline:
                                            self._loss_ptr + 4 * slot)
         if rc:
             _lib.check(rc, "pipeline_submit")
+        self._staged_last[slot] = False
 
     def submit_device(self, slot: int) -> None:
         """The step on the slot's current device buffers (no copies)."""
@@ -612,11 +614,37 @@ class HeadPipeline:
         dev = self.steps[0].device
         return tuple(torch.cuda.ExternalStream(p.value, device=dev) for p in ptrs)
 
+    def enable_staged(self) -> None:
+        """Staged mode: library-owned pinned host staging per slot + one CUDA graph per slot (this slot's
+        launches with the H2D of the NEXT slot's staged batch as a parallel branch): one driver call per step.
+        Fill `staging(k)` ahead of `submit_staged(k - 1)`; walk the slots round-robin."""
+        import numpy as np
+        _lib.check(self._lib.iif_pipeline_enable_staged(self._h), "pipeline_enable_staged")
+        self._staging = []
+        for k, hs in enumerate(self.steps):
+            px, py, pl = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _lib.check(self._lib.iif_pipeline_staging(self._h, k, C.byref(px), C.byref(py), C.byref(pl)), "pipeline_staging")
+            xb = (C.c_uint16 * (hs.B * hs.D)).from_address(px.value)
+            yb = (C.c_int64 * hs.B).from_address(py.value)
+            x = torch.from_numpy(np.frombuffer(xb, dtype=np.uint16).reshape(hs.B, hs.D)).view(torch.bfloat16)
+            y = torch.from_numpy(np.frombuffer(yb, dtype=np.int64))
+            self._staging.append((x, y, C.c_float.from_address(pl.value)))
+
+    def staging(self, slot: int):
+        """(x [B,D] bf16, label [B] int64): CPU tensors aliasing the slot's pinned staging buffers."""
+        return self._staging[slot][0], self._staging[slot][1]
+
+    def submit_staged(self, slot: int) -> None:
+        rc = self._lib.iif_pipeline_submit_staged(self._h, slot)
+        if rc:
+            _lib.check(rc, "pipeline_submit_staged")
+        self._staged_last[slot] = True
+
     def wait(self, slot: int) -> float:
         rc = self._lib.iif_pipeline_wait(self._h, slot)
         if rc:
             _lib.check(rc, "pipeline_wait")
-        return float(self.host_loss[slot])
+        return float(self._staging[slot][2].value) if self._staged_last[slot] else float(self.host_loss[slot])
 
     def stream_wait_step(self, slot: int, stream: torch.cuda.Stream) -> None:
         _lib.check(self._lib.iif_pipeline_stream_wait_step(self._h, slot, C.c_void_p(stream.cuda_stream)),

@@ -342,6 +342,17 @@ IIF_API int iif_pipeline_set_allreduce(iif_pipeline* p, void* const* peer_bufs_d
                                        int64_t n_elems, int num_ctas, int num_threads, int num_lanes);
 /* The pipeline's streams (cudaStream_t), e.g. to record timing events on them; any pointer may be NULL. */
 IIF_API int iif_pipeline_get_streams(iif_pipeline* p, void** h2d, void** compute, void** d2h, void** comm);
+/* Staged mode -- ONE driver call per step.  iif_pipeline_enable_staged gives every slot pinned HOST staging
+ * buffers (iif_pipeline_staging: x [B,D] bf16, label [B] int64, and the 4-byte loss, which the loss kernel
+ * stores straight into mapped pinned memory) and captures one CUDA graph per slot: this slot's two launches
+ * with the H2D copy of the NEXT slot's staged batch as a parallel branch.  Contract: slots are walked
+ * round-robin and, when slot k is submitted, slot k+1's staging already holds the following batch (a data
+ * loader one batch ahead); an out-of-order submit is still correct, it only pays an un-overlapped copy.
+ * iif_pipeline_wait(slot) then blocks until that step's loss is in *host_loss.  Not combined with
+ * iif_pipeline_set_allreduce. */
+IIF_API int iif_pipeline_enable_staged(iif_pipeline* p);
+IIF_API int iif_pipeline_staging(iif_pipeline* p, int slot, void** host_x, int64_t** host_label, float** host_loss);
+IIF_API int iif_pipeline_submit_staged(iif_pipeline* p, int slot);
 /* Block until the slot's latest step has delivered its loss to host_loss. */
 IIF_API int iif_pipeline_wait(iif_pipeline* p, int slot);
 /* Make `stream` wait for the slot's latest step (its gradients are then complete) ... */

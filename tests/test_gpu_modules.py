@@ -475,3 +475,51 @@ def test_normed_linear_head_shape_vs_oracle():
     assert rel_err(N(ops.row_dot(T(u), T(v))), (u.astype(np.float64) * v).sum(1)) < 1e-5
     out = ops.rows_axpby(T(u), T(pre), T(v), T(pre), T(pre))
     assert rel_err(N(out), pre[:, None] * u + (pre * pre)[:, None] * v) < 1e-6
+
+
+def test_head_pipeline_staged_mode():
+    """Staged mode (one CUDA graph per slot, next slot's batch prefetched inside the graph, loss stored by the
+    kernel into mapped pinned memory) reproduces the direct step for every batch, in order and out of order."""
+    from iif_b200.ops import HeadStep, HeadPipeline
+    B, D, C = 256, 512, 1000
+    bf = torch.bfloat16
+    x0, w, b, counts, y0 = head_inputs(B, D, C, seed=4)
+    iif = T(iif_row(counts, "raw")).reshape(-1)
+    wt, bt = T(w, bf), T(b)
+    nslots, nbatch = 3, 9
+    slots = []
+    for _ in range(nslots):
+        hs = HeadStep(B, D, C, DEV)
+        hs.bind(torch.zeros(B, D, dtype=bf, device=DEV), wt, bt, iif, torch.zeros(B, dtype=torch.int64, device=DEV))
+        slots.append(hs)
+    pipe = HeadPipeline(slots)
+    pipe.enable_staged()
+    rng = np.random.default_rng(1)
+    batches = [(torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32)).to(bf),
+                torch.from_numpy(lt_labels(counts, B, rng))) for _ in range(nbatch)]
+    ref = HeadStep(B, D, C, DEV)
+    want = []
+    for xb, yb in batches:
+        ref.bind(xb.to(DEV), wt, bt, iif, yb.to(DEV))
+        ref.launch()
+        torch.cuda.synchronize()
+        want.append((float(ref.loss), ref.dw.clone()))
+
+    def stage(k, i):
+        sx, sy = pipe.staging(k)
+        sx.copy_(batches[i][0]); sy.copy_(batches[i][1])
+
+    stage(0, 0)
+    for i in range(nbatch):                      # round-robin, the loader one batch ahead
+        k = i % nslots
+        if i + 1 < nbatch:
+            pipe.wait((i + 1) % nslots)          # the slot about to be restaged is idle
+            stage((i + 1) % nslots, i + 1)
+        pipe.submit_staged(k)
+        loss = pipe.wait(k)
+        torch.cuda.synchronize()
+        assert loss == want[i][0] and torch.equal(slots[k].dw, want[i][1])
+    stage(2, 4)                                  # out of order: slot 2 right after slot 2's turn was skipped
+    pipe.submit_staged(2)
+    assert pipe.wait(2) == want[4][0]
+    pipe.close()
