@@ -212,10 +212,21 @@ def main():
     ar_kind = "nccl"
     if world > 1 and args.allreduce != "nccl":
         from iif_b200.parallel import PeerAllReduce
-        peer = PeerAllReduce(C * D + C, S, dev, use_multicast=(args.allreduce == "peer"), num_ctas=args.ar_ctas,
-                             num_threads=args.ar_threads, lanes=args.ar_lanes)
-        ar_kind = "peer-memory kernel" + (" (NVLS multimem)" if peer.multicast else " (peer loads/stores)")
-        ar_kind += f", {peer.lanes} in flight"
+        try:
+            peer = PeerAllReduce(C * D + C, S, dev, use_multicast=(args.allreduce == "peer"), num_ctas=args.ar_ctas,
+                                 num_threads=args.ar_threads, lanes=args.ar_lanes)
+            ok = torch.ones(1, device=dev)
+        except RuntimeError as e:              # no peer mapping on this box: say so and use the NCCL arm
+            peer, ok = None, torch.zeros(1, device=dev)
+            if rank == 0:
+                print(f"# peer-memory all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank takes the same path
+        if float(ok.item()) == 0.0:
+            peer = None
+            ar_kind = "nccl (peer-memory all-reduce unavailable on this box)"
+        else:
+            ar_kind = "peer-memory kernel" + (" (NVLS multimem)" if peer.multicast else " (peer loads/stores)")
+            ar_kind += f", {peer.lanes} in flight"
     shared_ws = torch.zeros(max(int(ops._lib.load().iif_gemm_ws_bytes(B, D, C)), 1), dtype=torch.uint8, device=dev)
     for s in range(S):
         x = torch.randn(B, D, generator=g).to(dev).to(torch.bfloat16)
