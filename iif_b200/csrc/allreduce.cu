@@ -22,7 +22,7 @@ namespace iif {
 
 constexpr int AR_MAX_WORLD = 16;
 constexpr int AR_MAX_CTAS = 64;
-constexpr int AR_THREADS = 512;
+constexpr int AR_THREADS = 256;          // larger CTAs need an SM to themselves and have dead-locked against the GEMM grids
 constexpr int AR_LANES = 4;             // independent flag sets: up to 4 all-reduces of one rank may be in flight
 constexpr size_t AR_LANE_WORDS = (size_t)AR_MAX_CTAS * AR_MAX_WORLD + AR_MAX_CTAS;
 
@@ -50,10 +50,12 @@ __device__ __forceinline__ void ar_barrier(uint32_t* const* flags, size_t lane_o
     const uint32_t* mine = flags[rank] + slot + threadIdx.x;
     const long long t0 = clock64();
     uint32_t seen;
-    do {
+    for (;;) {
       asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-      if ((int32_t)(seen - value) < 0 && clock64() - t0 > 8000000000ll) ptx::wait_timed_out(1);
-    } while ((int32_t)(seen - value) < 0);
+      if ((int32_t)(seen - value) >= 0) break;
+      if (clock64() - t0 > 8000000000ll) ptx::wait_timed_out(1);
+      __nanosleep(200);                    // the SM is shared with a GEMM CTA of the overlapping step: poll politely
+    }
   }
   __syncthreads();
 }
@@ -91,7 +93,7 @@ __device__ __forceinline__ void ar_stamp(long long* dbg, int slot) {
 }
 
 template <bool MULTICAST, int U>
-__global__ void __launch_bounds__(AR_THREADS, 1)
+__global__ void __launch_bounds__(AR_THREADS, 2)
 allreduce_mean_kernel(float* const* bufs, uint32_t* const* flags, float* mc, int rank, int world, int64_t n4,
                       int64_t off4, int lane, long long* dbg) {
   ar_stamp(dbg, 0);

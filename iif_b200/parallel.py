@@ -103,6 +103,9 @@ class PeerAllReduce:
         self._check = _lib.check
         self.num_ctas = int(num_ctas) if num_ctas else 16
         self.num_threads = int(num_threads) if num_threads else 256
+        if self.num_threads > 256 or self.num_threads % 32:
+            raise ValueError("PeerAllReduce: num_threads must be a multiple of 32, at most 256 (a larger CTA needs an SM "
+                             "to itself and can dead-lock against the GEMM launches it overlaps)")
         # The all-reduce overlaps the next step's GEMM launches and blocks on other GPUs: keep its footprint
         # out of the resident-CTA budget their in-kernel rendezvous rely on (include/iif_b200.h).
         self.lanes = max(1, min(int(lanes), 4))     # all-reduces of consecutive steps that may be in flight at once
