@@ -109,7 +109,7 @@ class PeerAllReduce:
         # The all-reduce overlaps the next step's GEMM launches and blocks on other GPUs: keep its footprint
         # out of the resident-CTA budget their in-kernel rendezvous rely on (include/iif_b200.h).
         self.lanes = max(1, min(int(lanes), 4))     # all-reduces of consecutive steps that may be in flight at once
-        self._check(self._lib.iif_gemm_reserve_slots(self.lanes * self.num_ctas * (1 if self.num_threads <= 256 else 2)),
+        self._check(self._lib.iif_gemm_reserve_slots(self.lanes * self.num_ctas),
                     "gemm_reserve_slots")
         try:
             self.mem = symm_mem.empty(self.nbuf * self.stride, dtype=torch.float32, device=self.device)
