@@ -5,9 +5,13 @@
 
 One "step" = one pass of the hot path over one batch of synthetic features/labels:
 fc_cls GEMM -> IIF softmax-CE fwd+bwd -> db, dX, dW (bf16 GEMM operands, fp32 accumulate), through
-the C ABI (`iif_head_fwd_bwd_bf16`).  At N > 1 every rank processes its own B rows (weak scaling,
-row sharding) and the head's parameter gradients (dW, db: one flat fp32 buffer) are all-reduced
-(mean) over NCCL on a side stream, overlapping the next step's compute.
+the C ABI (`iif_head_fwd_bwd_bf16`: two launches, the loss rows ride in the backward launch).  At N > 1
+every rank processes its own B rows (weak scaling, row sharding) and the head's parameter gradients
+(dW, db: one flat fp32 buffer in peer-mapped memory) are all-reduced (mean) by the library's own
+NVLink kernel on side streams, overlapping the next steps' compute (`--allreduce nccl` = the NCCL arm).
+
+`e2e`: the same step through the host-batch API (`ops.HeadPipeline`): features + labels copied from
+pinned host memory and the loss brought back to the host every step.
 
 Timing hygiene: the step rotates through S independent sets of inputs AND outputs whose combined
 footprint exceeds the 126 MB L2, so no step finds its operands in L2 (config.l2 says so); CUDA

@@ -320,7 +320,7 @@ IIF_API int iif_head_launches(const iif_head_args* args);
  * `slot_args[i]` describes slot i's DEVICE buffers exactly as for iif_head_fwd_bwd_bf16 (x and label
  * are the device staging buffers the host batch is copied into; w, bias, iif are shared parameters;
  * ws may be shared by all slots).  Per submit: H2D of x [B,D] bf16 and label [B] int64 on a copy
- * stream, the three launches of the step on the library's single compute stream, D2H of the loss
+ * stream, the launches of the step (two, or three) on the library's single compute stream, D2H of the loss
  * scalar on a third stream -- slot i+1's copy overlaps slot i's kernels.  This is the data-loader ->
  * criterion(output, target) -> loss.item() sequence of cls/train.py:66-77 for the head alone.
  * ------------------------------------------------------------------------------------------- */
