@@ -192,7 +192,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int n0 = (tile % P.tiles_n) * BN, m0 = (tile / P.tiles_n) * TILE_M;
   // K blocks of a split tile are dealt round-robin: at any moment the `splits` CTAs of a tile stream ADJACENT
   // 128-byte chunks of the same operand rows (splits x 128 B contiguous per row) instead of chunks a quarter
-  // of a row apart -- friendlier to DRAM pages when the operands are cold.  Local index i -> block kb_of(i).
+  // of a row apart (measured neutral on B200 for the cold-HBM head shapes; kept because it makes every split
+  // non-empty for any split count).  Local index i -> block kb_of(i).
   const int kb_begin = 0;
   const int kb_end = (P.kb_total - split + ksp - 1) / ksp;                    // blocks split, split+S, split+2S, ...
   auto kb_of = [&](int i) { return split + i * ksp; };
