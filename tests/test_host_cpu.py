@@ -118,3 +118,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_bench_reads_committed_ncu_traffic():
+    """bench.py attaches the DRAM traffic of the dominant kernel from the committed ncu capture (profiles/)."""
+    import bench
+    t, src = bench.ncu_traffic("loss_linear_bwd_bf16", (256, 2048, 1000))
+    assert t is not None and 1e6 < t < 1e8 and "profiles/" in src
+    assert bench.ncu_traffic("loss_linear_bwd_bf16", (512, 2048, 1000)) == (None, None)
+    p = bench.peaks()
+    assert p["hbm"] > 1000 and p["tf_burst"] >= p["tf_sust"] > 100

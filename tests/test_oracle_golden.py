@@ -329,3 +329,48 @@ def test_cosnorm_golden(golden):
     close(z, g["cosnorm_z"], rtol=1e-9)
     close(dx, g["cosnorm_dx"], rtol=1e-9)
     close(dw, g["cosnorm_dw"], rtol=1e-9)
+
+
+# ------------------------------------------------------------------ size-independent properties of the oracle
+def test_oracle_properties_widened_rows():
+    """Properties the widened rows must satisfy whatever the size (they also guard the analytic backward
+    formulas of the oracle against a finite-difference check)."""
+    rng = np.random.default_rng(11)
+    B, C, D = 12, 20, 16
+    z = rng.standard_normal((B, C)) * 2
+    iif = rng.uniform(0.5, 6.0, (1, C))
+    ya, yb = rng.integers(0, C, B), rng.integers(0, C, B)
+    # Mixup: lam = 1 is the single-label loss, the loss is linear in lam, its gradient is the lam-mix
+    l1, d1 = ho.mixup_ce(z, iif, ya, yb, 1.0)
+    la, da, _ = ho.softmax_ce(z, iif, ya)
+    lb, db, _ = ho.softmax_ce(z, iif, yb)
+    np.testing.assert_allclose(l1, la, rtol=1e-12)
+    lh, dh = ho.mixup_ce(z, iif, ya, yb, 0.25)
+    np.testing.assert_allclose(lh, 0.25 * la + 0.75 * lb, rtol=1e-12)
+    np.testing.assert_allclose(dh, 0.25 * da + 0.75 * db, rtol=1e-12, atol=1e-15)
+    # focal: gamma -> 0 (no alpha) tends to plain BCE; finite differences of the loss match dz
+    lf, df = ho.focal_cls(z, ya, 1e-9)
+    lbce, dbce = ho.sigmoid_bce_cls(z, ya)
+    np.testing.assert_allclose(lf, lbce, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(df, dbce, rtol=1e-6, atol=1e-9)
+    eps = 1e-6
+    lf2, df2 = ho.focal_cls(z, ya, 2.0, 0.25)
+    zp = z.copy(); zp[3, 5] += eps
+    zm = z.copy(); zm[3, 5] -= eps
+    fd = (ho.focal_cls(zp, ya, 2.0, 0.25)[0].sum() - ho.focal_cls(zm, ya, 2.0, 0.25)[0].sum()) / (2 * eps)
+    assert abs(fd - df2[3, 5]) < 1e-6 * max(1.0, abs(fd))
+    # normalised classifiers: with eps = 0 and p = 1 the logits do not change when a feature row is rescaled;
+    # finite differences of <gz, z> match dx and dw
+    x = rng.standard_normal((B, D)); w = rng.standard_normal((C, D)) * 0.1; b = rng.standard_normal(C) * 0.1
+    gz = rng.standard_normal((B, C))
+    z0, dx, dw, dbb = ho.normed_linear(x, w, b, gz, temperature=20.0, power=1.0, eps=0.0)
+    z1 = ho.normed_linear(x * rng.uniform(0.5, 3.0, (B, 1)), w, b, gz, temperature=20.0, power=1.0, eps=0.0)[0]
+    np.testing.assert_allclose(z1, z0, rtol=1e-10, atol=1e-12)
+    f = lambda xx, ww: (ho.normed_linear(xx, ww, b, gz, 20.0, 1.5, 1e-3, iif=iif.reshape(-1))[0] * gz).sum()
+    _, dx2, dw2, _ = ho.normed_linear(x, w, b, gz, 20.0, 1.5, 1e-3, iif=iif.reshape(-1))
+    xp = x.copy(); xp[2, 7] += eps; xm = x.copy(); xm[2, 7] -= eps
+    assert abs((f(xp, w) - f(xm, w)) / (2 * eps) - dx2[2, 7]) < 1e-5 * max(1.0, abs(dx2[2, 7]))
+    wp = w.copy(); wp[4, 1] += eps; wm = w.copy(); wm[4, 1] -= eps
+    assert abs((f(x, wp) - f(x, wm)) / (2 * eps) - dw2[4, 1]) < 1e-5 * max(1.0, abs(dw2[4, 1]))
+    zc, dxc, dwc = ho.cosnorm_classifier(x, w, gz)
+    assert np.abs(zc).max() <= 16.0 + 1e-9          # |scale * cos| <= scale
