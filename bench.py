@@ -5,7 +5,7 @@
 
 One "step" = one pass of the hot path over one batch of synthetic features/labels:
 fc_cls GEMM -> IIF softmax-CE fwd+bwd -> db, dX, dW (bf16 GEMM operands, fp32 accumulate), through
-the C ABI (`iif_head_fwd_bwd_bf16`: two launches, the loss rows ride in the backward launch).  At N > 1
+the C ABI (`iif_head_fwd_bwd_bf16`: ONE persistent launch for the head shapes, csrc/head_fused.cu).  At N > 1
 every rank processes its own B rows (weak scaling, row sharding) and the head's parameter gradients
 (dW, db: one flat fp32 buffer in peer-mapped memory) are all-reduced (mean) by the library's own
 NVLink kernel on side streams, overlapping the next steps' compute (`--allreduce nccl` = the NCCL arm).
@@ -15,7 +15,14 @@ pinned host memory and the loss brought back to the host every step.
 
 Timing hygiene: the step rotates through S independent sets of inputs AND outputs whose combined
 footprint exceeds the 126 MB L2, so no step finds its operands in L2 (config.l2 says so); CUDA
-events on the launching stream, barrier + synchronize on both sides, max over ranks.
+events on the launching stream, barrier + synchronize on both sides, max over ranks.  The timed
+region of exactly `--steps` steps is repeated `repeats` times back to back (each repeat bracketed the
+same way, at N > 1 started from a device-side cross-rank barrier) and the MEDIAN is reported, so a
+20-step region (0.3 ms) is as stable as a long one; every set, graph and all-reduce lane is primed first.
+At N > 1 the library's all-reduce is checked against NCCL on live gradients before anything is timed
+(`allreduce_check`).  `torch_gpu_baseline` (N = 1) is the reference step in stock torch 2.11 on the same
+GPU (F.linear -> * iif -> F.cross_entropy -> backward; eager and CUDA-graph replay): the comparator
+SURVEY.md 8(d) calls "the real beat-this".
 
 `--impl reference` times the CPU arm: the fp32 torch restatement of the reference step
 (oracle/torch_port.py -- the reference's own Python cannot travel to the GPU box) on the host cores.
@@ -51,6 +58,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-loss", action="store_true", help="3 launches per step (loss rows in their own launch)")
+    ap.add_argument("--no-persistent", action="store_true", help="round-1 multi-launch step instead of the one persistent launch")
+    ap.add_argument("--repeats", type=int, default=0, help="timed regions of --steps steps (median reported); 0 = auto")
+    ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--no-e2e-alt", action="store_true", help="N=1: time only the staged host-batch mode")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--sync-allreduce", action="store_true", help="N>1: all-reduce on the compute stream (no overlap)")
     ap.add_argument("--ar-ctas", type=int, default=0)
@@ -126,8 +137,9 @@ def ncu_traffic(kernel, shape):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) of `kernel` for the ImageNet-LT shape,
     from profiles/r1_ncu_head_full_summary.csv (tools/gpu_profile.sh); None when there is no capture."""
     import csv
-    grid = {"linear_fwd_bf16": "128", "loss_linear_bwd_bf16": "256"}.get(kernel)
-    path = os.path.join(ROOT, "profiles", "r1_ncu_head_full_summary.csv")
+    grid = {"linear_fwd_bf16": "128", "loss_linear_bwd_bf16": "256", "head_step_fused_bf16": "148"}.get(kernel)
+    path = os.path.join(ROOT, "profiles", "r2_ncu_head_full_summary.csv" if kernel == "head_step_fused_bf16"
+                        else "r1_ncu_head_full_summary.csv")
     if shape != (256, 2048, 1000) or grid is None or not os.path.exists(path):
         return None, None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -141,7 +153,7 @@ def ncu_traffic(kernel, shape):
         return None, None
     if not vals:
         return None, None
-    return sum(vals) / len(vals), f"profiles/r1_ncu_head_full_summary.csv ({len(vals)} launches, ncu --set full, cold caches)"
+    return sum(vals) / len(vals), f"profiles/{os.path.basename(path)} ({len(vals)} launches, ncu --set full, cold caches)"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,9 +175,20 @@ def run_reference(args, B, D, C):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each "step" is one CPU head step; bound the whole run to a few minutes
+    # each "step" is one CPU head step; bound the whole run to a few minutes.  A 20-step region is ~50 ms of a
+    # 16-thread CPU GEMM -- dominated by thread wake-up noise -- so the timed region is repeated until it holds at
+    # least ~2 s of work and the MEDIAN region is reported (`repeats`).
+    from oracle import torch_port as tp
+    cores = len(os.sched_getaffinity(0))
     steps = max(1, min(args.steps, 2000))
-    r = cpu_arm(B, D, C, 0, steps=steps, warmup=max(3, min(args.warmup, 20)))
+    warm = max(3, min(args.warmup, 20))
+    probe = tp.time_head_step(B, D, C, steps=3, warmup=2, threads=cores)
+    repeats = int(max(1, min(25, round(2.0 / max(probe * steps, 1e-6)))))
+    runs = sorted(cpu_arm(B, D, C, 0, steps=steps, warmup=warm)["ms_per_step"] for _ in range(repeats))
+    r = cpu_arm(B, D, C, 0, steps=steps, warmup=warm)
+    med = runs[len(runs) // 2]
+    r["ms_per_step"], r["value"] = med, B / (med * 1e-3)
+    r["sample"] += f"; median of {repeats} repeats of the {steps}-step region"
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": max(3, min(args.warmup, 20)), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -173,8 +196,93 @@ def run_reference(args, B, D, C):
                        "note": "CPU arm: one process on the host cores, not sharded over GPUs"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "repeats": repeats}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# stock torch on the same GPU: the reference step as the reference's own ATen calls
+# ------------------------------------------------------------------------------------------------
+def torch_gpu_arm(B, D, C, dev, iif, prob, S, reps_target_s=0.25):
+    """F.linear -> * iif -> F.cross_entropy(mean) -> backward (dX, dW, db by autograd) in stock torch on `dev`,
+    over S rotating input sets (same L2 hygiene as our arm), CUDA events.  Two precisions: bf16 parameters and
+    activations (what apex-O2 / autocast training of the reference runs, cls/train.py:212-215) and the reference's
+    default fp32 (TF32 off); each eager and as CUDA-graph replay of the captured fwd+bwd."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    out = {}
+    prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for tag, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+            sets = []
+            for _ in range(S):
+                x = torch.randn(B, D, generator=g).to(dev).to(dt).requires_grad_(True)
+                w = ((torch.rand(C, D, generator=g) * 2 - 1) / D ** 0.5).to(dev).to(dt).requires_grad_(True)
+                b = torch.full((C,), 0.01, device=dev, dtype=dt).requires_grad_(True)
+                y = torch.multinomial(prob, B, replacement=True, generator=g).to(dev)
+                sets.append((x, w, b, y))
+            s_iif = iif.reshape(1, -1).float()
+
+            def step(k):
+                x, w, b, y = sets[k]
+                z = F.linear(x, w, b)
+                loss = F.cross_entropy(z.float() * s_iif, y)
+                loss.backward()
+                return loss
+
+            def clear(k):
+                for t in sets[k][:3]:
+                    t.grad = None
+
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            cur = torch.cuda.current_stream(dev)
+
+            def timed(fn, n):
+                torch.cuda.synchronize(dev)
+                ev0.record(cur)
+                for i in range(n):
+                    fn(i % S)
+                ev1.record(cur)
+                torch.cuda.synchronize(dev)
+                return ev0.elapsed_time(ev1) * 1e3 / n     # us per step
+
+            def eager(k):
+                clear(k)
+                step(k)
+
+            for k in range(S):
+                eager(k)
+            probe = timed(eager, 2 * S)
+            n = max(2 * S, min(4000, int(reps_target_s * 1e6 / max(probe, 1.0))))
+            us_eager = min(timed(eager, n) for _ in range(3))
+            # whole fwd+bwd captured per set (gradients become static tensors of the graph's pool)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for k in range(S):
+                    for _ in range(2):
+                        eager(k)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graphs = []
+            for k in range(S):
+                clear(k)
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    step(k)
+                graphs.append(gph)
+            us_graph = min(timed(lambda k: graphs[k].replay(), n) for _ in range(3))
+            out[tag] = {"eager_us_per_step": us_eager, "graph_us_per_step": us_graph,
+                        "eager_samples_per_s": B / (us_eager * 1e-6), "graph_samples_per_s": B / (us_graph * 1e-6)}
+            del graphs, sets
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+    out["what"] = ("stock torch %s on this GPU: F.linear -> z*iif -> F.cross_entropy(mean) -> backward, %d rotating sets, "
+                   "CUDA events; graph = torch.cuda.CUDAGraph replay of the captured fwd+bwd" % (torch.__version__, S))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -230,7 +338,7 @@ def main():
             ar_kind = "nccl (peer-memory all-reduce unavailable on this box)"
         else:
             ar_kind = "peer-memory kernel" + (" (NVLS multimem)" if peer.multicast else " (peer loads/stores)")
-            ar_kind += f", {peer.lanes} in flight"
+            ar_kind += f", {peer.num_ctas}x{peer.num_threads} threads, {peer.lanes} in flight"
     shared_ws = torch.zeros(max(int(ops._lib.load().iif_gemm_ws_bytes(B, D, C)), 1), dtype=torch.uint8, device=dev)
     for s in range(S):
         x = torch.randn(B, D, generator=g).to(dev).to(torch.bfloat16)
@@ -238,7 +346,8 @@ def main():
         y = torch.multinomial(prob, B, replacement=True, generator=g).to(dev)
         bias = torch.full((C,), 0.01, device=dev)
         hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws,
-                          fused_loss=not args.no_fused_loss, grad_flat=None if peer is None else peer.buffer(s))
+                          fused_loss=not args.no_fused_loss, persistent=not args.no_persistent,
+                          grad_flat=None if peer is None else peer.buffer(s))
         hs.bind(x, w, bias, iif, y)
         sets.append(hs)
     launches_per_step = sets[0].launches_per_step
@@ -246,8 +355,38 @@ def main():
     comm = torch.cuda.Stream(dev) if world > 1 else None
     ar_done = [None] * S
 
-    # ---- CUDA graphs: one per set (the kernels of one step); the all-reduce stays outside
+    def all_reduce(k, stream):
+        if peer is not None:
+            peer.all_reduce(k, stream)
+        else:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
+
+    # ---- N > 1, before anything is timed: the library's all-reduce against NCCL on the LIVE gradients of one step
+    ar_check = None
+    if world > 1:
+        sets[0].launch()
+        torch.cuda.synchronize(dev)
+        ref = sets[0].grad_flat.clone()
+        dist.all_reduce(ref, op=dist.ReduceOp.AVG)
+        all_reduce(0, cur)
+        torch.cuda.synchronize(dev)
+        got = sets[0].grad_flat
+        err = float(((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item())
+        bits = got.view(torch.int32).to(torch.int64)
+        sig = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=dev) % 8191 + 1)).sum()])
+        sigs = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        same = all(bool(torch.equal(t, sigs[0])) for t in sigs)
+        ar_check = {"max_rel_err_vs_nccl_avg": err, "identical_on_all_ranks": same, "elements": int(got.numel()),
+                    "kind": ar_kind, "ok": bool(err <= 1e-6 and same)}
+        if not ar_check["ok"]:
+            raise RuntimeError(f"all-reduce check failed on rank {rank}: {ar_check}")
+
+    # ---- CUDA graphs (N = 1 / --py-loop): one per set, plus ONE ring graph holding a step of every set so that
+    # consecutive steps are consecutive kernel nodes (no per-step graph-launch gap)
     graphs = [None] * S
+    ring = None
     use_graph = not args.no_graph
     if use_graph:
         side = torch.cuda.Stream(dev)
@@ -262,14 +401,12 @@ def main():
             with torch.cuda.graph(gph):
                 hs.launch()
             graphs[i] = gph
+        if world == 1:
+            ring = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ring):
+                for hs in sets:
+                    hs.launch()
         torch.cuda.synchronize(dev)
-
-    def all_reduce(k, stream):
-        if peer is not None:
-            peer.all_reduce(k, stream)
-        else:
-            with torch.cuda.stream(stream):
-                dist.all_reduce(sets[k].grad_flat, op=dist.ReduceOp.AVG)
 
     def step(i):
         k = i % S
@@ -293,18 +430,24 @@ def main():
 
     # N > 1 with the peer-memory all-reduce: the whole loop runs through the C pipeline (one call per step
     # enqueues the step on its compute stream and the all-reduce of its gradients on its comm stream), so
-    # the host is not the bottleneck of a 30 us step; events are recorded on the pipeline's own streams.
+    # the host is not the bottleneck of a ~15 us step; events are recorded on the pipeline's own streams.
     pipe_main = None
+    p_compute = None
     if world > 1 and peer is not None and not args.sync_allreduce and not args.py_loop:
         pipe_main = ops.HeadPipeline(sets)
         pipe_main.set_allreduce(peer)
-        _, p_compute, _, p_comm = pipe_main.streams()
+        _, p_compute, _, _ = pipe_main.streams()
         use_graph = False
 
     def run_steps(n):
         if pipe_main is not None:
             for i in range(n):
                 pipe_main.submit_device(i % S)
+        elif ring is not None:
+            for _ in range(n // S):               # S consecutive steps (sets 0..S-1) per graph launch
+                ring.replay()
+            for i in range(n % S):
+                graphs[i].replay()
         else:
             for i in range(n):
                 step(i)
@@ -317,30 +460,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    run_steps(max(args.warmup, 3))
+    # prime EVERY set, graph and all-reduce lane (the timed region must not absorb first-touch costs)
+    warm = max(args.warmup, 3, S + 4 if world > 1 else 3)
+    run_steps(warm)
     fence()
+    tstream = p_compute if pipe_main is not None else cur
+    tok = torch.zeros(1, device=dev)
+    repeats = args.repeats if args.repeats > 0 else int(max(3, min(25, round(60000 / max(args.steps, 1)))))
     n0 = ops.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0s = [torch.cuda.Event(enable_timing=True) for _ in range(repeats)]
+    e1s = [torch.cuda.Event(enable_timing=True) for _ in range(repeats)]
+    region_ms = []
     with ClockSampler(local) as clk:
-        if pipe_main is not None:
-            e0.record(p_compute)
-            run_steps(args.steps)
-            p_comm.wait_stream(p_compute)       # the last all-reduce is ordered after the last step anyway
-            e1.record(p_comm)
-        else:
-            e0.record(cur)
-            run_steps(args.steps)
+        for r in range(repeats):
+            fence()                                     # barrier + synchronize before ...
             if world > 1:
+                # ... and a DEVICE-side cross-rank barrier right in front of the start event: every rank's timed
+                # stream is released by the same collective, not by the host's view of a barrier
+                with torch.cuda.stream(tstream):
+                    dist.all_reduce(tok)
+            e0s[r].record(tstream)
+            run_steps(args.steps)
+            if pipe_main is not None:
+                pipe_main.join(tstream)                 # the compute stream waits for EVERY comm lane
+            elif world > 1:
                 cur.wait_stream(comm)
-            e1.record(cur)
-        fence()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+            e1s[r].record(tstream)
+            fence()                                     # ... and after the timed region
+            ms_r = e0s[r].elapsed_time(e1s[r])
+            if world > 1:
+                t = torch.tensor([ms_r], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_r = float(t.item())
+            region_ms.append(ms_r)
+    ms = statistics.median(region_ms)
     launched = ops.launch_count() - n0
-    gpu_launches = args.steps * launches_per_step if use_graph else launched
+    gpu_launches = args.steps * launches_per_step if use_graph else launched // repeats
     value = world * B * args.steps / (ms * 1e-3)
     loss_val = float(sets[(args.steps - 1) % S].loss)
 
@@ -386,10 +541,10 @@ def main():
         if world > 1:
             comm.synchronize()
 
-    n_e2e = min(args.steps, 3000)
+    n_e2e = max(200, min(args.steps, 3000))
 
     def e2e_time():
-        e2e_run(32)
+        e2e_run(max(32, S + 4))
         fence()
         t0 = time.perf_counter()
         e2e_run(n_e2e)
@@ -400,12 +555,12 @@ def main():
     # N = 1: both host-batch modes of the public API are timed -- the staged mode costs one driver call per step
     # (robust on a slow / shared host) but pays the GPU-side gap between graph launches; the event-driven mode
     # costs ~11 driver calls per step and wins on a fast host.  The faster one is reported, the other kept.
-    e2e_ms = e2e_time()
+    e2e_ms = min(e2e_time() for _ in range(3))
     e2e_alt = None
-    if staged:
+    if staged and not args.no_e2e_alt:
         staged_ms = e2e_ms
         staged = False
-        e2e_ms = e2e_time()
+        e2e_ms = min(e2e_time() for _ in range(3))
         e2e_alt = {"staged_ms_per_step": staged_ms / n_e2e, "event_driven_ms_per_step": e2e_ms / n_e2e}
         if staged_ms < e2e_ms:
             e2e_ms, staged = staged_ms, True
@@ -433,9 +588,14 @@ def main():
             # loss rows + dX + dW + db in one launch: Z in, dZ out (its re-read comes from L2), X, W in, dX, dW, db out
             "loss_linear_bwd_bf16": (4 * B * C + 2 * B * C + 16 * B + 4 * C + e * C * D + e * B * D + e * B * D
                                      + 4 * C * D + 4 * C, 4.0 * B * D * C),
+            # the whole step in one launch: X, W, labels, bias, iif in; Z (fp32, an API output), dZ (bf16, an API
+            # output), dX, dW, db out -- SURVEY.md 8(d) Q_ideal + the two outputs the drop-in API keeps
+            "head_step_fused_bf16": (e * B * D + e * C * D + 8 * B + 8 * C + 4 * B * C + 2 * B * C + e * B * D
+                                     + 4 * C * D + 4 * C + 4 * B, 6.0 * B * D * C),
         }
         names = [n for n, _ in sets[0].kernels()]
         reps = max(1, 1200 // S)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for j, name in enumerate(names):
             fns = [hs.kernels()[j][1] for hs in sets]
             for f in fns:
@@ -469,11 +629,15 @@ def main():
         for k in kern:
             k["share"] = k["us"] / tot
         top = max(kern, key=lambda k: k["us"])
+        # T_roof of the drop-in 4-kernel form (fwd, loss, dX, dW), sustained tensor peak
+        q4 = [(e * (B * D + C * D) + 4 * B * C + 8 * C, 2.0 * B * D * C), (8 * B * C + 16 * B + 4 * C, 0.0),
+              (4 * B * C + e * C * D + e * B * D, 2.0 * B * D * C), (4 * B * C + e * B * D + 4 * C * D + 4 * C, 2.0 * B * D * C)]
+        t_roof4 = sum(max(by / (pk["hbm"] * 1e9), fl / (pk["tf_sust"] * 1e12)) for by, fl in q4) * 1e6
         roofline = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
                     "frac": top["frac"], "traffic": None, "kernel": top["kernel"], "us_per_launch": top["us"],
                     "peak_source": pk["src"] + (" burst" if top["bound"] == "tensor" else " copy"),
-                    "step_roofline_us": sum(max(k["algo_bytes"] / (pk["hbm"] * 1e9), k["flops"] / (pk["tf_sust"] * 1e12))
-                                            for k in kern) * 1e6}
+                    "step_roofline_us": t_roof4,
+                    "step_roofline_def": "BASELINE.md s3: sum over {fwd, loss, dX, dW} of max(bytes/HBM, flops/sustained bf16)"}
         roofline["step_frac"] = roofline["step_roofline_us"] / (ms * 1e3 / args.steps)
         roofline["traffic"], roofline["traffic_source"] = ncu_traffic(top["kernel"], (B, D, C))
         roofline["algo_bytes"] = top["algo_bytes"]
@@ -481,20 +645,29 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_arm(B, D, C, args.cpu_seconds)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        tgb = None
+        if world == 1 and not args.no_torch_baseline:
+            tgb = torch_gpu_arm(B, D, C, dev, iif, prob, S)
+            tgb["ours_over_torch_graph_bf16"] = value / tgb["bf16"]["graph_samples_per_s"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "repeats": repeats, "region_ms": {"median": ms, "min": min(region_ms), "max": max(region_ms)},
                 "config": {"workload": WORKLOAD if (B, D, C) == (256, 2048, 1000) else f"IIF head {B}x{D}x{C}",
                            "B_per_gpu": B, "D": D, "C": C, "global_batch": B * world, "variant": args.variant,
                            "parallelism": f"dp{world} (row sharding, {ar_kind} all-reduce(mean) of dW+db "
                                           f"{'on the compute stream' if args.sync_allreduce else 'overlapped on a side stream'})"
                                           if world > 1 else "dp1",
-                           "launch": (f"cuda-graph replay (one graph = the {launches_per_step} launches of a step)"
-                                      if use_graph else ("eager, one C call per step (iif_pipeline_submit_device)"
-                                                         if pipe_main is not None else "eager")),
+                           "launch": (f"cuda-graph replay (one graph = one step of each of the {S} sets, "
+                                      f"{launches_per_step} launch(es) per step)"
+                                      if ring is not None else
+                                      (f"cuda-graph replay (one graph = the {launches_per_step} launches of a step)"
+                                       if use_graph else ("eager, one C call per step (iif_pipeline_submit_device)"
+                                                          if pipe_main is not None else "eager"))),
                            "l2": f"rotating {S} independent input+output sets, {S * per_set / 1e6:.0f} MB > 126 MB L2"},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
-                "kernels": kern, "cpu_baseline": cpu, "loss": loss_val}
+                "kernels": kern, "cpu_baseline": cpu, "torch_gpu_baseline": tgb, "allreduce_check": ar_check,
+                "loss": loss_val}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

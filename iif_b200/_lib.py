@@ -15,6 +15,7 @@ OK, EINVAL, EALIGN, EUNSUPPORTED, EWORKSPACE, EDRIVER = 0, -1, -2, -3, -4, -5
 VARIANT_IDS = {"raw": 0, "smooth": 1, "rel": 2, "prob": 2, "normit": 3, "gombit": 4, "base2": 5, "base10": 6}
 DTYPE_F32, DTYPE_BF16 = 0, 1
 HEAD_NO_FUSED_LOSS = 1
+HEAD_NO_PERSISTENT = 2
 NORM_NORMED, NORM_COS, NORM_UNIT = 0, 1, 2
 
 _p, _i64, _i32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t
@@ -65,13 +66,17 @@ SIGNATURES = {
     "iif_linear_bwd_bf16": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i32, _i64, _p, _i64, _p, _i64, _i64, _i64, _p,
                                    _sz, _p]),
     "iif_debug_timing": (None, [_p]),
+    "iif_debug_timing_fused": (None, [_p]),
+    "iif_debug_fused_plan": (_i32, [_i64, _i64, _i64, _i32, _i32, _p]),
     "iif_debug_timing_allreduce": (None, [_p]),
     "iif_debug_capacity": (_i32, [_p]),
     "iif_allreduce_mean_f32": (_i32, [_p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _i32, _p]),
     "iif_allreduce_flag_bytes": (_sz, []),
+    "iif_allreduce_set_timeout_ms": (_i32, [_i64]),
     "iif_pipeline_create": (_i32, [C.POINTER(_p), C.POINTER(HeadArgs), _i32]),
     "iif_pipeline_submit": (_i32, [_p, _i32, _p, _p, _p]),
     "iif_pipeline_submit_device": (_i32, [_p, _i32]),
+    "iif_pipeline_join": (_i32, [_p, _p]),
     "iif_pipeline_set_allreduce": (_i32, [_p, _p, _p, _p, _i32, _i32, C.POINTER(_i64), _i64, _i32, _i32, _i32]),
     "iif_pipeline_get_streams": (_i32, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
     "iif_pipeline_enable_staged": (_i32, [_p]),
@@ -84,6 +89,7 @@ SIGNATURES = {
     "iif_pipeline_destroy": (None, [_p]),
     "iif_gemm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "iif_gemm_reserve_slots": (_i32, [_i32]),
+    "iif_gemm_assume_exclusive": (_i32, [_i32]),
     "iif_head_fwd_bwd_bf16": (_i32, [C.POINTER(HeadArgs), _p]),
     "iif_loss_linear_bwd_bf16": (_i32, [C.POINTER(HeadArgs), _p]),
     "iif_head_launches": (_i32, [C.POINTER(HeadArgs)]),

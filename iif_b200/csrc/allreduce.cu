@@ -15,6 +15,8 @@
 // against 2x that for a ring; latency: two NVLink round trips instead of 2 (world-1) ring steps.
 //
 // Flags: a zero-initialised symmetric uint32 array [cta][peer] of monotonically growing values (see ar_barrier).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -37,8 +39,18 @@ constexpr size_t AR_LANE_WORDS = (size_t)AR_MAX_CTAS * AR_MAX_WORLD + AR_MAX_CTA
 // gradients it announces were written by the PREVIOUS kernel of the stream, and nothing read after either
 // handshake can be stale -- peer data is read with ld.cv / multimem (never from a cached copy), and the
 // reduced result is consumed by later kernels out of this GPU's own L2.
+//
+// The poll is an INTER-GPU wait: ranks of a data-parallel job skew by far more than a kernel's lifetime (a
+// checkpoint or an evaluation on rank 0, a data-loader stall, a time-sliced GPU), so its bound is wall-clock
+// (%globaltimer, which keeps its meaning across preemption), minutes by default and configurable / removable:
+// iif_allreduce_set_timeout_ms, env IIF_B200_PEER_TIMEOUT_S (0 = wait forever, like NCCL without a watchdog).
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void ar_barrier(uint32_t* const* flags, size_t lane_off, int rank, int world, uint32_t value,
-                                           bool release) {
+                                           bool release, unsigned long long timeout_ns) {
   __syncthreads();
   const size_t slot = lane_off + (size_t)blockIdx.x * AR_MAX_WORLD;
   if (threadIdx.x == 0) {
@@ -48,13 +60,19 @@ __device__ __forceinline__ void ar_barrier(uint32_t* const* flags, size_t lane_o
   }
   if ((int)threadIdx.x < world) {
     const uint32_t* mine = flags[rank] + slot + threadIdx.x;
-    const long long t0 = clock64();
-    uint32_t seen;
+    unsigned long long t0 = 0;
+    uint32_t seen, spins = 0;
     for (;;) {
       asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
       if ((int32_t)(seen - value) >= 0) break;
-      if (clock64() - t0 > 8000000000ll) ptx::wait_timed_out(1);
-      __nanosleep(200);                    // the SM is shared with a GEMM CTA of the overlapping step: poll politely
+      if (++spins > 64) {                  // first ~64 polls back to back (the common case: the peer is microseconds away)
+        __nanosleep(100);                  // then politely: the SM is shared with a CTA of the overlapping step
+        if (timeout_ns && (spins & 1023u) == 0) {
+          const unsigned long long now = global_ns();
+          if (!t0) t0 = now;
+          else if (now - t0 > timeout_ns) ptx::wait_timed_out(3);
+        }
+      }
     }
   }
   __syncthreads();
@@ -95,13 +113,13 @@ __device__ __forceinline__ void ar_stamp(long long* dbg, int slot) {
 template <bool MULTICAST, int U>
 __global__ void __launch_bounds__(AR_THREADS, 2)
 allreduce_mean_kernel(float* const* bufs, uint32_t* const* flags, float* mc, int rank, int world, int64_t n4,
-                      int64_t off4, int lane, long long* dbg) {
+                      int64_t off4, int lane, long long* dbg, unsigned long long timeout_ns) {
   ar_stamp(dbg, 0);
   const size_t lane_off = (size_t)lane * AR_LANE_WORDS;
   // launch number of this CTA (stream-ordered launches: no race), stored next to the flags
   uint32_t* epoch_p = flags[rank] + lane_off + (size_t)AR_MAX_CTAS * AR_MAX_WORLD + blockIdx.x;
   const uint32_t epoch = *epoch_p + 1;
-  ar_barrier(flags, lane_off, rank, world, 2 * epoch, false);
+  ar_barrier(flags, lane_off, rank, world, 2 * epoch, false, timeout_ns);
   if (threadIdx.x == 0) *epoch_p = epoch;
   ar_stamp(dbg, 1);
   const int64_t per = (n4 + world - 1) / world;                    // float4 per rank slice
@@ -155,7 +173,7 @@ allreduce_mean_kernel(float* const* bufs, uint32_t* const* flags, float* mc, int
     }
   }
   ar_stamp(dbg, 2);
-  ar_barrier(flags, lane_off, rank, world, 2 * epoch + 1, true);            // release: our peer stores land before the "done" flag
+  ar_barrier(flags, lane_off, rank, world, 2 * epoch + 1, true, timeout_ns);            // release: our peer stores land before the "done" flag
   ar_stamp(dbg, 3);
 }
 
@@ -165,6 +183,23 @@ using namespace iif;
 
 static long long* g_ar_dbg = nullptr;
 extern "C" void iif_debug_timing_allreduce(long long* buf) { g_ar_dbg = buf; }
+
+static std::atomic<long long> g_ar_timeout_ms{-1};       // -1: not set (env IIF_B200_PEER_TIMEOUT_S, else 600 s); 0: wait forever
+extern "C" int iif_allreduce_set_timeout_ms(int64_t ms) {
+  if (ms < 0) return IIF_EINVAL;
+  g_ar_timeout_ms.store(ms, std::memory_order_relaxed);
+  return IIF_OK;
+}
+static unsigned long long ar_timeout_ns() {
+  long long ms = g_ar_timeout_ms.load(std::memory_order_relaxed);
+  if (ms < 0) {
+    const char* e = getenv("IIF_B200_PEER_TIMEOUT_S");
+    ms = e ? (long long)(atof(e) * 1e3) : 600000ll;
+    if (ms < 0) ms = 0;
+    g_ar_timeout_ms.store(ms, std::memory_order_relaxed);
+  }
+  return (unsigned long long)ms * 1000000ull;
+}
 
 extern "C" size_t iif_allreduce_flag_bytes(void) {
   return AR_LANES * AR_LANE_WORDS * sizeof(uint32_t);   // per lane: [cta][peer] flags + [cta] launch numbers
@@ -186,9 +221,10 @@ extern "C" int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* p
   cudaStream_t st = (cudaStream_t)stream;
   float* mc = reinterpret_cast<float*>(multicast_ptr);
   const int64_t n4 = n_elems / 4, off4 = offset_elems / 4;
-  if (mc) allreduce_mean_kernel<true, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg);
-  else if (world <= 2) allreduce_mean_kernel<false, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg);
-  else if (world <= 4) allreduce_mean_kernel<false, 4><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg);
-  else allreduce_mean_kernel<false, 2><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg);
+  const unsigned long long tmo = ar_timeout_ns();
+  if (mc) allreduce_mean_kernel<true, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo);
+  else if (world <= 2) allreduce_mean_kernel<false, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo);
+  else if (world <= 4) allreduce_mean_kernel<false, 4><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo);
+  else allreduce_mean_kernel<false, 2><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo);
   return launch_status();
 }

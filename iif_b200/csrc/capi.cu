@@ -21,12 +21,18 @@ extern "C" const char* iif_error_string(int code) {
   }
 }
 
-// fc_cls -> IIF softmax-CE fwd+bwd -> {dX, dW, db} on one stream: 2 launches when the loss rows can ride in
-// the backward launch (iif_loss_linear_bwd_bf16), else 3.
+// fc_cls -> IIF softmax-CE fwd+bwd -> {dX, dW, db} on one stream: ONE persistent launch when the shape qualifies
+// (head_fused.cu), else 2 launches when the loss rows can ride in the backward launch (iif_loss_linear_bwd_bf16),
+// else 3.
 extern "C" int iif_head_fwd_bwd_bf16(const iif_head_args* h, void* stream) {
   if (!h || !h->x || !h->w || !h->label || !h->z || !h->dz_bf16 || !h->dw) return IIF_EINVAL;
   if (h->lddz % 8 != 0) return IIF_EALIGN;
-  int rc = iif_linear_fwd_bf16(h->x, h->ldx, h->w, h->ldw, h->bias, nullptr, h->z, h->ldz, nullptr, 0, h->B, h->D, h->C,
+  int rc;
+  if (!(h->flags & IIF_HEAD_NO_PERSISTENT)) {          // the whole step in ONE persistent launch (head_fused.cu)
+    rc = iif::head_fused_launch(h, stream, false);
+    if (rc != IIF_EUNSUPPORTED) return rc;
+  }
+  rc = iif_linear_fwd_bf16(h->x, h->ldx, h->w, h->ldw, h->bias, nullptr, h->z, h->ldz, nullptr, 0, h->B, h->D, h->C,
                                h->ws, h->ws_bytes, stream);
   if (rc) return rc;
   if (!(h->flags & IIF_HEAD_NO_FUSED_LOSS)) {

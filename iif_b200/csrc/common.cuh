@@ -13,9 +13,13 @@ extern std::atomic<uint64_t> g_launches;  // defined in capi.cu
 
 inline int launch_status() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaPeekAtLastError();
+  cudaError_t e = cudaGetLastError();   // clears a non-sticky launch error: it is reported once, by the launch that caused it
   return e == cudaSuccess ? IIF_OK : (int)e;
 }
+
+// internal entry points of the one-launch head step (head_fused.cu), called by capi.cu / gemm_tc.cu
+size_t head_fused_ws_bytes(int64_t B, int64_t D, int64_t C);
+int head_fused_launch(const iif_head_args* h, void* stream, bool dry_run);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

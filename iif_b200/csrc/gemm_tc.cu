@@ -54,6 +54,7 @@
 #include "common.cuh"
 #include "loss_row.cuh"
 #include "ptx.cuh"
+#include "tc_common.cuh"
 
 namespace iif {
 
@@ -74,7 +75,7 @@ __host__ __device__ constexpr int smem_bytes_for(int stages) {
 }
 constexpr int SMEM_BYTES = smem_bytes_for(MIN_STAGES);       // the 2-CTAs-per-SM configuration
 constexpr int GEN_PITCH = 65;         // generic epilogue: warp-private 32 x 65 float slab
-constexpr int WS_HEADER = 8192;       // split-K counters: 2 problems x 256 tiles x {arrive, done}; grid barrier at 4096
+constexpr int WS_HEADER = 16384;      // [0, 4096) split-K counters: 2 problems x 256 tiles; grid barrier at 4096; [8192, 16384) counters of head_fused.cu
 constexpr int TILE_F4 = TILE_M * BN / 4;
 // Split-K arrival counters never reset: every CTA of a tile adds EPOCH_UNIT / splits, so each launch
 // advances the tile's counter by exactly EPOCH_UNIT whatever its split count (840 = lcm(1..8)); the
@@ -527,67 +528,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
-struct MapKey {
-  const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer, f32;
-  bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
-           box_outer == o.box_outer && f32 == o.f32;
-  }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.ptr);
-    for (uint64_t v : {k.inner, k.outer, k.ld, (uint64_t)k.box_inner, (uint64_t)k.box_outer, (uint64_t)k.f32})
-      h = h * 1000003u ^ (size_t)v;
-    return h;
-  }
-};
-
-// Row-major [outer, inner] tensor (bf16 or fp32) with leading dimension ld (elements); box =
-// box_inner x box_outer with a 128-byte inner extent, 128B swizzle.  Loads: out-of-bounds elements
-// read as zero (tile tails need no host padding); stores: out-of-bounds elements are not written.
-static int make_map(CUtensorMap* out, const void* ptr, bool f32, uint64_t inner, uint64_t outer, uint64_t ld,
-                    uint32_t box_inner, uint32_t box_outer) {
-  static std::mutex mu;
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{ptr, inner, outer, ld, box_inner, box_outer, f32 ? 1u : 0u};
-  {
-    std::lock_guard<std::mutex> g(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) { *out = it->second; return IIF_OK; }
-  }
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return IIF_EDRIVER;
-  const cuuint64_t dims[2] = {inner, outer};
-  const cuuint64_t strides[1] = {ld * (f32 ? 4u : 2u)};
-  const cuuint32_t box[2] = {box_inner, box_outer};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return IIF_EDRIVER;
-  std::lock_guard<std::mutex> g(mu);
-  if (cache.size() > 4096) cache.clear();
-  cache.emplace(key, *out);
-  return IIF_OK;
-}
-
 // Resident-CTA capacity of the device for this kernel (2 per SM on B200): the split-K rendezvous
 // needs every CTA of the grid on an SM at the same time.
 static const void* kernel_variant(int v) {
@@ -727,17 +667,30 @@ static int fill_problem(const GemmDesc& d, const Plan& p, float* partial, unsign
 
 static long long* g_dbg = nullptr;   // iif_debug_timing
 static std::atomic<int> g_reserved_slots{0};   // iif_gemm_reserve_slots
+// In-kernel rendezvous (split-K, the loss-fused backward's grid barrier) need every CTA of the grid resident at
+// once.  By default they are only used in grids the driver accepts as COOPERATIVE launches (co-residency
+// guaranteed whatever else runs on the device; kernels of other streams can delay such a launch, never dead-lock
+// it).  iif_gemm_assume_exclusive(1) additionally allows larger grids -- up to this library's own resident-CTA
+// bound -- for callers that guarantee nothing else occupies the SMs while the head's launches run.
+static std::atomic<int> g_exclusive{0};
 
 // Launch one or two problems in one grid.
 static int launch_group(const GemmDesc* d_in, int nprob, void* ws, size_t ws_bytes, cudaStream_t st,
                         const RowArgs* loss = nullptr, bool dry_run = false) {
   GemmDesc d[2];
   for (int i = 0; i < nprob; ++i) d[i] = d_in[i];
-  int cap = resident_capacity();
+  int detail[6];
+  int cap = resident_capacity(detail);
   if (cap <= 0) { cudaGetLastError(); return IIF_EDRIVER; }
-  // resident-CTA slots promised to kernels that overlap these launches AND block on other GPUs (the
-  // all-reduce): the in-kernel rendezvous may only count on the rest
-  cap -= g_reserved_slots.load(std::memory_order_relaxed);
+  const int coop_cap = (detail[0] > 0 ? detail[0] : 1) * kNumSMs;   // what a cooperative launch of this kernel may hold
+  const bool exclusive = g_exclusive.load(std::memory_order_relaxed) != 0;
+  if (exclusive) {
+    // resident-CTA slots promised to kernels that overlap these launches AND block on other GPUs (the
+    // all-reduce): the in-kernel rendezvous may only count on the rest
+    cap -= g_reserved_slots.load(std::memory_order_relaxed);
+  } else if (cap > coop_cap) {
+    cap = coop_cap;
+  }
   if (cap < 1) cap = 1;
   TcGroup g{};
   CUtensorMap maps[6] = {};
@@ -843,13 +796,20 @@ static int launch_group(const GemmDesc* d_in, int nprob, void* ws, size_t ws_byt
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem_bytes_for(g.stages);
   cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
-  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = 1;
   void* kargs[7] = {&maps[0], &maps[1], &maps[2], &maps[3], &maps[4], &maps[5], &g};
-  cudaError_t e = cudaLaunchKernelExC(&cfg, kernel_variant(variant), kargs);
+  const bool rendezvous = any_split || loss != nullptr;
+  cudaError_t e;
+  if (rendezvous && cta <= coop_cap) {
+    e = launch_cooperative(cfg, kernel_variant(variant), kargs, true);
+  } else {
+    if (rendezvous && !exclusive) return IIF_EUNSUPPORTED;   // (the planner keeps rendezvous grids within coop_cap)
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelExC(&cfg, kernel_variant(variant), kargs);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return (int)e;
   return IIF_OK;
@@ -893,13 +853,18 @@ extern "C" int iif_gemm_reserve_slots(int slots) {
   return IIF_OK;
 }
 extern "C" int iif_debug_capacity(int* detail6) { return resident_capacity(detail6); }
+extern "C" int iif_gemm_assume_exclusive(int on) {
+  g_exclusive.store(on ? 1 : 0, std::memory_order_relaxed);
+  return IIF_OK;
+}
 
 extern "C" size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C) {
   if (B <= 0 || D <= 0 || C <= 0) return 0;
   // Upper bound over every launch of the head: split-K never runs more than 2 x 148 CTAs, each
   // parking one 64 KB partial tile (+ 512 B of db partials), plus the counter header.
-  (void)D;
-  return (size_t)WS_HEADER + (size_t)(2 * kNumSMs) * (TILE_M * BN * 4 + TILE_M * 4);
+  const size_t multi = (size_t)WS_HEADER + (size_t)(2 * kNumSMs) * (TILE_M * BN * 4 + TILE_M * 4);
+  const size_t fused = head_fused_ws_bytes(B, D, C);      // the one-launch step parks more partial tiles for some shapes
+  return fused > multi ? fused : multi;
 }
 
 extern "C" int iif_linear_fwd_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
@@ -980,6 +945,11 @@ extern "C" int iif_loss_linear_bwd_bf16(const iif_head_args* h, void* stream) { 
 // launch) or 3; negative = argument error.
 extern "C" int iif_head_launches(const iif_head_args* h) {
   if (!h) return IIF_EINVAL;
+  if (!(h->flags & IIF_HEAD_NO_PERSISTENT)) {
+    const int rf = head_fused_launch(h, nullptr, true);
+    if (rf == IIF_OK) return 1;
+    if (rf != IIF_EUNSUPPORTED) return rf;
+  }
   if (h->flags & IIF_HEAD_NO_FUSED_LOSS) return 3;
   const int rc = loss_linear_bwd(h, nullptr, true);
   if (rc == IIF_OK) return 2;

@@ -4,6 +4,8 @@
 #pragma once
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -113,6 +115,11 @@ __device__ __forceinline__ bool grid_tail(double part, int c1, int c5, float* lo
 // Small batches use wide rows (TPR = C/4: one 128-bit load per thread, short dependency chains, every
 // SM busy); large batches use NE = 8 for more bytes in flight per SM.
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
+// ZLoad: where the vec body gets a float4 of raw logits from.  NoZLoad = the logits tensor a.z (streaming
+// 128-bit loads); the fused head step passes a functor that sums the forward GEMM's split-K partial tiles
+// instead (head_fused.cu) -- it is called as zload(col, row) for in-range float4 groups only and must
+// return -inf for elements at or beyond column C.
+struct NoZLoad {};
 
 template <int THREADS>
 struct RowSmem {
@@ -132,10 +139,10 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2: 2 ulp, exp2
 // out-of-row elements are encoded as z = -inf, s = 1 (so no per-element bounds logic survives the loads),
 // the label's column is found with one range test per float4, optional outputs (argmax / rank) sit behind
 // warp-uniform branches, exp is one FMUL + MUFU.EX2 on (a - max) * log2(e).
-template <int TPR, int NE, int MODE, class Hook>
+template <int TPR, int NE, int MODE, class Hook, class ZLoad = NoZLoad>
 __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t row_block,
                                                      RowSmem<(TPR > 256 ? TPR : 256)>& sm, float& my_loss_out,
-                                                     int& cnt_out, bool& active_out, Hook hook) {
+                                                     int& cnt_out, bool& active_out, Hook hook, ZLoad zload = ZLoad()) {
   constexpr int THREADS = TPR > 256 ? TPR : 256;
   constexpr int WPR = TPR / 32;
   constexpr int NQ = NE / 4;
@@ -185,13 +192,20 @@ __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t r
   float4 z4[NQ], s4[CACHE_S ? NQ : 1];
   auto load_s = [&](int q) -> float4 {
     const int col = (q * TPR + t) * 4;
-    return (a.iif && active && col < C) ? __ldg(reinterpret_cast<const float4*>(a.iif + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    if (!(a.iif && active && col < C)) return make_float4(1.f, 1.f, 1.f, 1.f);
+    if (col + 4 <= C) return __ldg(reinterpret_cast<const float4*>(a.iif + col));
+    // ragged last group (C % 4 != 0: only reachable through a ZLoad functor): no read past the vector's end
+    return make_float4(__ldg(a.iif + col), col + 1 < C ? __ldg(a.iif + col + 1) : 1.f, col + 2 < C ? __ldg(a.iif + col + 2) : 1.f, 1.f);
   };
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int col = (q * TPR + t) * 4;
-    z4[q] = (active && col < C) ? ldg_stream4(zr + col)
-                                : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    if constexpr (std::is_same<ZLoad, NoZLoad>::value)
+      z4[q] = (active && col < C) ? ldg_stream4(zr + col)
+                                  : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    else
+      z4[q] = (active && col < C) ? zload(col, row)
+                                  : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
     if constexpr (CACHE_S) s4[q] = load_s(q);
   }
 

@@ -17,6 +17,7 @@ struct iif_pipeline {
     iif_head_args a;
     cudaEvent_t h2d_done, step_done, loss_done, release;
     bool used, held;
+    bool device_only;                  // latest step came from submit_device: no loss was copied to the host
     int64_t ar_offset;
     // staged mode (iif_pipeline_enable_staged): library-owned pinned host staging + one CUDA graph per slot
     void* host_x; int64_t* host_y; float* host_loss;   // pinned; host_loss is mapped (the kernel stores into it)
@@ -123,13 +124,32 @@ extern "C" int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x
   IIF_CU(cudaMemcpyAsync(host_loss, a.loss_sum, 4, cudaMemcpyDeviceToHost, p->s_d2h));
   IIF_CU(cudaEventRecord(s.loss_done, p->s_d2h));
   s.used = true;
+  s.device_only = false;
   return IIF_OK;
 }
 
 // Same step with the inputs ALREADY in the slot's device buffers (no copies): the device-resident loop.
 extern "C" int iif_pipeline_submit_device(iif_pipeline* p, int slot) {
   if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  p->slots[slot].device_only = true;
   return run_step(p, p->slots[slot]);
+}
+
+// Make `stream` wait (on the device) for everything the pipeline has enqueued so far: the compute stream, the copy
+// streams and EVERY comm lane -- e.g. to record a timing event after the last all-reduce of a timed region.
+extern "C" int iif_pipeline_join(iif_pipeline* p, void* stream) {
+  if (!p) return IIF_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t ev;
+  IIF_CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaStream_t all[7] = {p->s_h2d, p->s_compute, p->s_d2h, p->s_comm[0], p->s_comm[1], p->s_comm[2], p->s_comm[3]};
+  for (cudaStream_t s : all) {
+    if (s == st) continue;
+    IIF_CU(cudaEventRecord(ev, s));
+    IIF_CU(cudaStreamWaitEvent(st, ev, 0));
+  }
+  IIF_CU(cudaEventDestroy(ev));
+  return IIF_OK;
 }
 
 extern "C" int iif_pipeline_get_streams(iif_pipeline* p, void** h2d, void** compute, void** d2h, void** comm) {
@@ -234,11 +254,13 @@ extern "C" int iif_pipeline_submit_staged(iif_pipeline* p, int slot) {
   iif::g_launches.fetch_add((uint64_t)s.launches, std::memory_order_relaxed);
   p->primed = (slot + 1) % p->nslots;
   s.used = true;
+  s.device_only = false;
   return IIF_OK;
 }
 
 extern "C" int iif_pipeline_wait(iif_pipeline* p, int slot) {
   if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
+  if (p->slots[slot].device_only) return IIF_EINVAL;   // submit_device copies no loss back: nothing to wait for
   if (!p->slots[slot].used) return IIF_OK;
   IIF_CU(cudaEventSynchronize(p->slots[slot].loss_done));
   return IIF_OK;

@@ -10,11 +10,22 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Bound of the INTRA-GPU waits (mbarrier phases, flags between CTAs of one co-resident grid), in SM cycles: such
+// a wait ends within microseconds unless a descriptor / byte count / counter is wrong, and then a trap the host
+// sees beats a hung GPU.  ~10 s at 2 GHz, so a debugger stop or a time-sliced context does not trip it; build with
+// -DIIF_INTRA_WAIT_CYCLES=<n> to change it.  (Waits on OTHER GPUs are bounded separately and in wall-clock time:
+// allreduce.cu.)
+#ifndef IIF_INTRA_WAIT_CYCLES
+#define IIF_INTRA_WAIT_CYCLES 20000000000ll
+#endif
+
 // Cold path of every bounded wait: kept out of line so the hot code stays compact in the instruction cache.
 __device__ __noinline__ inline void wait_timed_out(int what) {
   printf("iif_b200: %s timed out (block %d thread %d)%s\n",
-         what == 0 ? "mbarrier wait" : (what == 1 ? "inter-CTA flag wait" : "split-K rendezvous"), blockIdx.x, threadIdx.x,
-         what == 0 ? "" : ": workspace header not zeroed?");
+         what == 0 ? "mbarrier wait" : (what == 1 ? "inter-CTA flag wait" : (what == 2 ? "split-K rendezvous" : "inter-GPU flag wait")),
+         blockIdx.x, threadIdx.x,
+         what == 0 ? "" : (what == 3 ? ": a peer rank never arrived (iif_allreduce_set_timeout_ms / IIF_B200_PEER_TIMEOUT_S)"
+                                     : ": workspace header not zeroed?"));
   __trap();
 }
 
@@ -51,7 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) wait_timed_out(0);
+    if (clock64() - t0 > IIF_INTRA_WAIT_CYCLES) wait_timed_out(0);
   }
 }
 
@@ -93,6 +104,8 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk groups of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all committed bulk groups of this thread are COMPLETE: their global writes have been performed
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -133,14 +146,14 @@ __device__ __forceinline__ void spin_until_ge(const int* p, int target) {
   if (ld_acquire(p) >= target) return;
   const long long t0 = clock64();
   while (ld_acquire(p) < target) {
-    if (clock64() - t0 > 4000000000ll) wait_timed_out(1);
+    if (clock64() - t0 > IIF_INTRA_WAIT_CYCLES) wait_timed_out(1);
   }
 }
 __device__ __forceinline__ void spin_until_ge_u64(const unsigned long long* p, unsigned long long target) {
   if (ld_acquire_u64(p) >= target) return;
   const long long t0 = clock64();
   while (ld_acquire_u64(p) < target) {
-    if (clock64() - t0 > 4000000000ll) wait_timed_out(2);
+    if (clock64() - t0 > IIF_INTRA_WAIT_CYCLES) wait_timed_out(2);
   }
 }
 

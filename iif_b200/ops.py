@@ -437,7 +437,7 @@ class HeadStep:
     (`grad_flat`) so the data-parallel all-reduce of the head's parameter gradients is one message."""
 
     def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False, ws=None,
-                 fused_loss=True, grad_flat=None):
+                 fused_loss=True, grad_flat=None, persistent=True):
         dev = torch.device(device)
         self.B, self.D, self.C, self.device = B, D, Cc, dev
         f32, i32 = torch.float32, torch.int32
@@ -464,7 +464,8 @@ class HeadStep:
         self.ws_bytes = n
         self.dx_dtype = _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32
         self.fused_loss = bool(fused_loss)
-        self.launches_per_step = 3     # refined by bind(): 2 when the loss rows ride in the backward launch
+        self.persistent = bool(persistent)   # the whole step in ONE persistent launch when the shape qualifies
+        self.launches_per_step = 3     # refined by bind(): 1 = persistent step, 2 = loss rows ride in the backward launch
         self._args = None
         self._keep = None
 
@@ -506,7 +507,7 @@ class HeadStep:
         a.acc_counts = None if self.acc_counts is None else self.acc_counts.data_ptr()
         a.scratch = self.scratch.data_ptr()
         a.ws, a.ws_bytes = self.ws.data_ptr(), self.ws_bytes
-        a.flags = 0 if self.fused_loss else _lib.HEAD_NO_FUSED_LOSS
+        a.flags = (0 if self.fused_loss else _lib.HEAD_NO_FUSED_LOSS) | (0 if self.persistent else _lib.HEAD_NO_PERSISTENT)
         n = int(_lib.load().iif_head_launches(C.byref(a)))
         if n < 0:
             _lib.check(n, "head_launches")
@@ -533,6 +534,8 @@ class HeadStep:
         lib, a = _lib.load(), self._args
         st = lambda: _stream(self.device)
         p = C.c_void_p
+        if self.launches_per_step == 1:
+            return [("head_step_fused_bf16", lambda: lib.iif_head_fwd_bwd_bf16(C.byref(a), st()))]
         out = [("linear_fwd_bf16", lambda: lib.iif_linear_fwd_bf16(p(a.x), a.ldx, p(a.w), a.ldw, p(a.bias), None,
                                                                    p(a.z), a.ldz, None, 0, a.B, a.D, a.C, p(a.ws),
                                                                    a.ws_bytes, st()))]
@@ -592,6 +595,10 @@ class HeadPipeline:
         rc = self._lib.iif_pipeline_submit_device(self._h, slot)
         if rc:
             _lib.check(rc, "pipeline_submit_device")
+
+    def join(self, stream: torch.cuda.Stream) -> None:
+        """Make `stream` wait on the device for everything enqueued so far on all of the pipeline's streams."""
+        _lib.check(self._lib.iif_pipeline_join(self._h, C.c_void_p(stream.cuda_stream)), "pipeline_join")
 
     def set_allreduce(self, peer) -> None:
         """Data-parallel runs: all-reduce(mean) every step's gradients with `peer` (parallel.PeerAllReduce whose

@@ -257,6 +257,8 @@ IIF_API int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int
  * it off.  iif_debug_capacity: resident-CTA capacity of the current device for the tensor-core kernel
  * (the split-K rendezvous is only enabled for grids that fit it). */
 IIF_API void iif_debug_timing(long long* buf);
+IIF_API void iif_debug_timing_fused(long long* buf);       /* one-launch step: 16 int64 per CTA, see tools/tc_timing.py */
+IIF_API int iif_debug_fused_plan(int64_t B, int64_t D, int64_t C, int need_dx, int sms, int* out12);   /* host only: the one-launch step's plan */
 IIF_API void iif_debug_timing_allreduce(long long* buf);   /* 8 int64 per CTA: start, after handshake, after data, end */
 IIF_API int iif_debug_capacity(int* detail6 /* host, optional: occupancy API, by smem, by regs, regs, smem/SM, static smem */);
 
@@ -267,6 +269,11 @@ IIF_API int iif_debug_capacity(int* detail6 /* host, optional: occupancy API, by
  * planner only counts on the remaining slots (falling back to unsplit / unfused launches when a grid no
  * longer fits). */
 IIF_API int iif_gemm_reserve_slots(int slots);
+/* By default the launches that rendezvous inside a grid are only made as COOPERATIVE launches (the driver
+ * guarantees co-residency whatever else runs on the device), which bounds such grids by the runtime's own
+ * occupancy answer.  A caller that guarantees exclusive use of the SMs while the head's launches run may allow
+ * the larger grids of round 1 (up to this library's own resident-CTA bound, minus iif_gemm_reserve_slots). */
+IIF_API int iif_gemm_assume_exclusive(int on);
 
 /* Workspace (bytes) the three bf16 GEMMs of a head of this shape may need (max over the three). */
 IIF_API size_t iif_gemm_ws_bytes(int64_t B, int64_t D, int64_t C);
@@ -305,6 +312,7 @@ typedef struct iif_head_args {
  * chained by programmatic dependent launch (cls/train.py:66-77 collapsed to the head;
  * seg/.../bbox_head.py:118 + :269-274 + autograd). */
 #define IIF_HEAD_NO_FUSED_LOSS 1      /* keep the loss rows in their own launch (3 launches per step) */
+#define IIF_HEAD_NO_PERSISTENT 2      /* do not use the one-launch persistent step (csrc/head_fused.cu) */
 IIF_API int iif_head_fwd_bwd_bf16(const iif_head_args* args, void* stream);
 /* The loss rows + AddmmBackward in ONE launch: every CTA of the backward launch first computes its share
  * of the softmax-CE rows (reads args->z, writes loss_i / dz_bf16 / argmax / rank), the grid meets at a
@@ -330,8 +338,12 @@ IIF_API int iif_pipeline_create(iif_pipeline** out, const iif_head_args* slot_ar
  * contiguous, host_label: [B] int64, host_loss: 4 bytes; all three should be pinned. Never blocks. */
 IIF_API int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x, const int64_t* host_label,
                                 float* host_loss);
-/* The same step with the inputs already in the slot's device buffers (no copies, no loss read-back). */
+/* The same step with the inputs already in the slot's device buffers (no copies, no loss read-back:
+ * iif_pipeline_wait on such a slot returns IIF_EINVAL until it is submitted with host batches again). */
 IIF_API int iif_pipeline_submit_device(iif_pipeline* p, int slot);
+/* Make `stream` wait, on the device, for everything enqueued so far on ALL of the pipeline's streams
+ * (compute, copies, every comm lane). */
+IIF_API int iif_pipeline_join(iif_pipeline* p, void* stream);
 /* Data-parallel runs: after every step, all-reduce(mean) the slot's gradient slice with
  * iif_allreduce_mean_f32 on the pipeline's comm stream (arguments as there; slot i's slice starts at
  * slot_offsets_elems[i]); the slot is not reused before its all-reduce has finished.  num_lanes (1..4)
@@ -382,6 +394,9 @@ IIF_API int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* peer
                                    int rank, int world, int64_t offset_elems, int64_t n_elems, int num_ctas,
                                    int num_threads /* 0 = defaults */, int lane /* 0..3 */, void* stream);
 IIF_API size_t iif_allreduce_flag_bytes(void);
+/* Bound of the kernel's waits on OTHER ranks, wall-clock milliseconds (default 600 000, or the environment
+ * variable IIF_B200_PEER_TIMEOUT_S at first use; 0 = wait forever).  Past it the kernel reports and traps. */
+IIF_API int iif_allreduce_set_timeout_ms(int64_t ms);
 
 #ifdef __cplusplus
 }

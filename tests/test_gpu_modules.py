@@ -305,19 +305,25 @@ def test_loss_fused_into_backward_launch(B, D, C):
     bit-identical dZ / loss_i / argmax / rank and the same loss, dX, dW, db as the 3-launch chain; the
     workspace counters re-arm themselves (several steps back to back on one workspace)."""
     from iif_b200.ops import HeadStep
+    from iif_b200 import _lib
     x, w, b, counts, y = head_inputs(B, D, C, seed=B + C)
     iif = iif_row(counts, "raw")
     y[::7] = -100                                     # ignored rows
     bf = torch.bfloat16
     args = (T(x, bf), T(w, bf), T(b), T(iif).reshape(-1), T(y))
-    a = HeadStep(B, D, C, DEV, want_acc=True, fused_loss=True)
-    u = HeadStep(B, D, C, DEV, want_acc=True, fused_loss=False)
-    a.bind(*args); u.bind(*args)
-    assert u.launches_per_step == 3
-    assert a.launches_per_step == 2, "this shape is expected to qualify for the fused launch"
-    for _ in range(3):
-        la, lu = a.launch(), u.launch()
-    torch.cuda.synchronize()
+    a = HeadStep(B, D, C, DEV, want_acc=True, fused_loss=True, persistent=False)
+    u = HeadStep(B, D, C, DEV, want_acc=True, fused_loss=False, persistent=False)
+    # these grids exceed what the driver admits as a cooperative launch: only legal with the SMs to ourselves
+    _lib.load().iif_gemm_assume_exclusive(1)
+    try:
+        a.bind(*args); u.bind(*args)
+        assert u.launches_per_step == 3
+        assert a.launches_per_step == 2, "this shape is expected to qualify for the fused launch"
+        for _ in range(3):
+            la, lu = a.launch(), u.launch()
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().iif_gemm_assume_exclusive(0)
     assert torch.equal(a.z, u.z) and torch.equal(a.dz[:, :C], u.dz[:, :C]) and torch.equal(a.loss_i, u.loss_i)
     assert torch.equal(a.argmax, u.argmax) and torch.equal(a.rank, u.rank) and torch.equal(a.acc_counts, u.acc_counts)
     assert float(la) == pytest.approx(float(lu), rel=1e-6)
