@@ -52,6 +52,12 @@ SIGNATURES = {
                                        _p, _i64, _p, _p]),
     "iif_sigmoid_focal_fwd_bwd": (_i32, [_p, _i64, _p, _f32, _f32, _p, _p, _i64, _f32, _i64, _i64, _p, _i64, _p, _p, _p, _i64,
                                          _p, _i64, _p, _p]),
+    "iif_sigmoid_bce_dense_fwd_bwd": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _f32, _i64, _i64, _p, _i64, _p, _p, _p, _i64,
+                                             _p, _p]),
+    "iif_class_accumulate": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "iif_class_feature_stats": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _f32, _p, _p, _i64, _p, _p, _p]),
+    "iif_class_feature_stats_ws_bytes": (_sz, [_i64]),
+    "iif_shot_accuracy": (_i32, [_p, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "iif_row_scale_from_norm": (_i32, [_p, _i64, _i64, _i64, _p, _i32, _f32, _f32, _f32, _p, _p, _p, _p]),
     "iif_row_dot": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _p, _p]),
     "iif_rows_axpby": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _p, _i64, _p]),

@@ -107,28 +107,57 @@ class Mixup(object):
         return lam * self.criterion(pred, y_a) + (1 - lam) * self.criterion(pred, y_b)
 
 
+class NormedLinear(nn.Module):
+    """classification/resnet_cifar.py:38-48 (`--classif_norm norm`, resnet_pytorch.py:212-219):
+    out = F.normalize(x, dim=1) @ F.normalize(weight, dim=0), weight stored [in_features, out_features] and
+    initialised uniform(-1,1).renorm_(2,1,1e-5).mul_(1e5); `bias` exists (random) but is NOT used in forward -- both as
+    in the reference.  The operand normalisations (F.normalize: v / max(|v|, 1e-12)) and their backward run in the
+    library's row kernels, the contraction in the head's GEMMs (`compute` = 'bf16' tensor cores | 'fp32')."""
+
+    def __init__(self, in_features, out_features, compute="bf16", device="cuda"):
+        super().__init__()
+        self.compute = compute
+        self.weight = nn.Parameter(torch.empty(in_features, out_features, device=device))
+        self.weight.data.uniform_(-1, 1).renorm_(2, 1, 1e-5).mul_(1e5)
+        self.bias = nn.Parameter(torch.randn(out_features, device=device))
+
+    def forward(self, x):
+        from . import _lib
+        ex = F_.normalize_rows(x, _lib.NORM_UNIT, temperature=1.0, eps=1e-12)
+        # columns of the [in, out] weight = rows of its transpose (the GEMM's [C, D] operand)
+        ew = F_.normalize_rows(self.weight.t(), _lib.NORM_UNIT, temperature=1.0, eps=1e-12)
+        return F_.linear(ex, ew, None, bf16=(self.compute == "bf16"))
+
+
 class CosNorm_Classifier(nn.Module):
     """classification/resnet_cifar.py:50-78: z = scale * (x / (1 + |x|)) . (w / |w|)^T  (no bias).  The two
     operand normalisations and their backward run in the library's row kernels, the contraction in the head's
-    GEMMs (`compute` = 'bf16' tensor cores | 'fp32').  `lr_scale=True` (a learnable scale, squared) is not
-    provided."""
+    GEMMs (`compute` = 'bf16' tensor cores | 'fp32').  `lr_scale=True` (`--classif_norm lr_cosine`): the scale is a
+    learnable parameter initialised to 5.0 and applied SQUARED (:56-57,75-76)."""
 
     def __init__(self, in_dims, out_dims, scale=16, margin=0.5, init_std=0.001, lr_scale=False, compute="bf16",
                  device="cuda"):
         super().__init__()
-        if lr_scale:
-            raise NotImplementedError("CosNorm_Classifier(lr_scale=True) is not provided")
         import math
         self.in_features, self.out_dims, self.lr_scale = in_dims, out_dims, lr_scale
-        self.scale, self.margin, self.compute = scale, margin, compute
+        if lr_scale is True:
+            self.scale = nn.Parameter(5.0 * torch.ones(1, device=device))
+        else:
+            self.scale = scale
+        self.margin, self.compute = margin, compute
         self.weight = nn.Parameter(torch.empty(out_dims, in_dims, device=device))
         stdv = 1.0 / math.sqrt(in_dims)
         self.weight.data.uniform_(-stdv, stdv)
 
     def forward(self, input, *args):
         from . import _lib
-        ex = F_.normalize_rows(input, _lib.NORM_COS, temperature=float(self.scale))
         ew = F_.normalize_rows(self.weight, _lib.NORM_UNIT, temperature=1.0, eps=0.0)
+        if self.lr_scale is True:
+            # z = scale^2 * (ex . ew): the learnable factor multiplies the product (one scalar, autograd by torch:
+            # d/dscale = 2 scale <gz, z0>), the operands stay normalised with T = 1
+            ex = F_.normalize_rows(input, _lib.NORM_COS, temperature=1.0)
+            return F_.linear(ex, ew, None, bf16=(self.compute == "bf16")) * (self.scale ** 2)
+        ex = F_.normalize_rows(input, _lib.NORM_COS, temperature=float(self.scale))
         return F_.linear(ex, ew, None, bf16=(self.compute == "bf16"))
 
 
@@ -138,6 +167,27 @@ def accuracy(output, target, topk=(1,)):
         r = ops.softmax_ce(output.float(), None, target, want_dz_f32=False, want_acc=True, want_sum=False)
         B = target.size(0)
         return [(r["rank"] < k).sum(dtype=torch.float32) * (100.0 / B) for k in topk]
+
+
+def shot_acc(preds, labels, train_targets, many_shot_thr=100, low_shot_thr=20, acc_per_cls=False):
+    """classification/per_shot_acc.py:62-105: mean class accuracy over the many- / median- / low-shot classes (by TRAIN
+    count) among the classes present in `labels`.  `preds` / `labels`: CUDA tensors [n]; `train_targets`: the training
+    labels (CUDA tensor / array: histogrammed on the device) .  Per-class counts are integer kernels (bit-exact), the
+    three means one small reduction; returns python floats like the reference (np.mean), plus the per-class
+    accuracies of the present classes (in class order, like np.unique) when `acc_per_cls`."""
+    import numpy as np
+    dev = preds.device
+    tt = torch.as_tensor(np.asarray(train_targets) if not isinstance(train_targets, torch.Tensor) else train_targets)
+    tt = tt.to(dev).reshape(-1).long()
+    labels = labels.reshape(-1).long()
+    n_cls = int(max(int(labels.max()) if labels.numel() else 0, int(tt.max()) if tt.numel() else 0)) + 1
+    train_counts = ops.hist_labels(tt, n_cls)
+    r = ops.shot_accuracy(preds, labels, train_counts, many_shot_thr, low_shot_thr, want_class_acc=acc_per_cls)
+    many, med, low = (float(v) for v in r[0].cpu())
+    if acc_per_cls:
+        ca = r[3].cpu().numpy()
+        return many, med, low, [float(v) for v in ca[ca >= 0]]
+    return many, med, low
 
 
 def predictions(output, iif=None):

@@ -75,7 +75,7 @@ __host__ __device__ constexpr int smem_bytes_for(int stages) {
 }
 constexpr int SMEM_BYTES = smem_bytes_for(MIN_STAGES);       // the 2-CTAs-per-SM configuration
 constexpr int GEN_PITCH = 65;         // generic epilogue: warp-private 32 x 65 float slab
-constexpr int WS_HEADER = 16384;      // [0, 4096) split-K counters: 2 problems x 256 tiles; grid barrier at 4096; [8192, 16384) counters of head_fused.cu
+constexpr int WS_HEADER = 32768;      // [0, 4096) split-K counters: 2 problems x 256 tiles; grid barrier at 4096; [8192, 32768) counters of head_fused.cu
 constexpr int TILE_F4 = TILE_M * BN / 4;
 // Split-K arrival counters never reset: every CTA of a tile adds EPOCH_UNIT / splits, so each launch
 // advances the tile's counter by exactly EPOCH_UNIT whatever its split count (840 = lcm(1..8)); the

@@ -24,12 +24,18 @@
 // loss.backward()) and seg/mmdet/models/roi_heads/bbox_heads/bbox_head.py:118,269-274 + autograd.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
 #include "loss_row.cuh"
 #include "ptx.cuh"
 #include "tc_common.cuh"
+
+#ifndef HF_MIN_BLOCKS
+#define HF_MIN_BLOCKS 1
+#endif
 
 namespace iif {
 namespace hf {
@@ -44,10 +50,17 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + ONES_BYTES + B
 constexpr int TMEM_COLS = 256;                 // 128 accumulator columns + 16 for db (power of two)
 constexpr int TILE_F4 = TM * TN / 4;
 constexpr int MAX_SPLITS = 8;
-// counters (int32) in the workspace header, bytes [8192, 16384): zero between launches
+// Counters (int32) in the workspace header, bytes [8192, 32768).  Word 0 = parity; two counter SETS follow: launch k
+// works on set (parity) and its last CTA to arrive at the grid barrier zeroes the other set -- used by launch k - 1,
+// complete by then -- and flips the parity for launch k + 1.  No launch ever resets a counter another CTA may still
+// poll, so nothing at the end of the kernel waits for "everybody is done".
 constexpr int CTR_BYTE_OFFSET = 8192;
+constexpr int CTR_SET0 = 64, CTR_SET_STRIDE = 2560;
 constexpr int CTR_ROWS = 0, CTR_READY_F = 8, CTR_DX = 128;
-constexpr int MAX_MT = 96, MAX_DX_TILES = 1024;
+constexpr int MAX_MT = 96, MAX_DX_TILES = 2048;
+constexpr int WS_HEADER_BYTES = 32768;
+static_assert(CTR_BYTE_OFFSET + (CTR_SET0 + 2 * CTR_SET_STRIDE) * 4 <= WS_HEADER_BYTES, "counter sets must fit the header");
+static_assert(CTR_DX + MAX_DX_TILES <= CTR_SET_STRIDE && CTR_READY_F + MAX_MT <= CTR_DX, "counter set layout");
 
 struct Gemm { int M, N, K, tiles_m, tiles_n, kb_total, splits, items; };
 
@@ -62,6 +75,7 @@ struct Args {
   void* dx_out; int dx_bf16; int64_t lddx;
   float* db;
   long long* dbg;
+  int flags;                 // debug switches (env IIF_B200_FUSED_FLAGS): 1 = writer-side proxy fences as in round 1
 };
 
 struct Item {
@@ -77,7 +91,7 @@ __device__ __forceinline__ void stamp(const Args& g, int slot) {
   if (g.dbg) {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g.dbg[(int64_t)blockIdx.x * 16 + slot] = t;
+    g.dbg[(int64_t)blockIdx.x * 32 + slot] = t;
   }
 }
 
@@ -125,62 +139,93 @@ __device__ __forceinline__ int my_items(int n) {   // how many items of an n-ite
   return k;
 }
 
-// Sum of the forward partial tiles of one float4 of a logit row, + bias: the raw logits Z (also written out).
-struct PartialZ {
-  const float4* part; const float* bias; float* z; int64_t ldz; int C, tiles_n, S; bool zvec;
-  __device__ __forceinline__ float4 operator()(int col, int64_t row) const {
-    const int mi = (int)(row >> 7), r = (int)(row & 127), ni = col >> 7, cc = col & 127;
-    const float4* p = part + ((int64_t)(mi * tiles_n + ni) * S * TM + r) * (TN / 4) + (cc >> 2);
-    float4 t[MAX_SPLITS];
+// The raw logits of this thread's share of a row: sum of the forward partial tiles in split order (deterministic)
+// + bias; also written out as Z.  All loads of a group of QG float4 columns are issued before the first one is
+// consumed (one L2 round trip per group instead of one per float4); columns at or beyond C come back as -inf.
+template <int TPR, int NE>
+__device__ __forceinline__ void load_bias(const Args& g, bool active, float4 (&b4)[NE / 4]) {
+  const int t = threadIdx.x % TPR, C = g.loss.C;
 #pragma unroll
-    for (int s = 0; s < MAX_SPLITS; ++s)
-      if (s < S) t[s] = __ldcg(p + (int64_t)s * TILE_F4);
-    float4 acc = t[0];
-#pragma unroll
-    for (int s = 1; s < MAX_SPLITS; ++s)           // fixed split order: deterministic
-      if (s < S) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }
-    const bool full = col + 4 <= C;
-    if (bias) {
-      if (full) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
-        acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
-      } else {
-        acc.x += __ldg(bias + col);
-        if (col + 1 < C) acc.y += __ldg(bias + col + 1);
-        if (col + 2 < C) acc.z += __ldg(bias + col + 2);
-      }
-    }
-    if (z) {
-      float* o = z + row * ldz + col;
-      if (full && zvec) stg_stream4(o, acc);
+  for (int q = 0; q < NE / 4; ++q) {
+    const int col = (q * TPR + t) * 4;
+    b4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.bias && active && col < C) {
+      if (col + 4 <= C) b4[q] = __ldg(reinterpret_cast<const float4*>(g.bias + col));
       else {
-        o[0] = acc.x;
-        if (col + 1 < C) o[1] = acc.y;
-        if (col + 2 < C) o[2] = acc.z;
-        if (col + 3 < C) o[3] = acc.w;
+        b4[q].x = __ldg(g.bias + col);
+        if (col + 1 < C) b4[q].y = __ldg(g.bias + col + 1);
+        if (col + 2 < C) b4[q].z = __ldg(g.bias + col + 2);
       }
     }
-    if (!full) {                                   // ragged last group: columns >= C do not exist
-      if (col + 1 >= C) acc.y = -CUDART_INF_F;
-      if (col + 2 >= C) acc.z = -CUDART_INF_F;
-      acc.w = -CUDART_INF_F;
-    }
-    return acc;
   }
-};
+}
+template <int TPR, int NE>
+__device__ __forceinline__ void load_logits(const Args& g, int64_t row, bool active, const float4 (&b4)[NE / 4],
+                                            float4 (&z4)[NE / 4]) {
+  constexpr int NQ = NE / 4;
+  constexpr int QG = NQ < 2 ? NQ : 2;                // float4 columns per batch: QG x MAX_SPLITS loads in flight
+  const int t = threadIdx.x % TPR, C = g.loss.C, S = g.f.splits;
+  const int mi = (int)(row >> 7), r = (int)(row & 127);
+  float* zrow = g.loss.z ? const_cast<float*>(g.loss.z) + row * g.loss.ldz : nullptr;
+  const bool zvec = (g.loss.ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(g.loss.z) & 15u) == 0;
+#pragma unroll
+  for (int q0 = 0; q0 < NQ; q0 += QG) {
+    float4 tt[QG][MAX_SPLITS];
+#pragma unroll
+    for (int u = 0; u < QG; ++u) {
+      const int col = ((q0 + u) * TPR + t) * 4;
+      if (active && col < C) {
+        const float4* p = g.part + ((int64_t)(mi * g.f.tiles_n + (col >> 7)) * S * TM + r) * (TN / 4) + ((col & 127) >> 2);
+#pragma unroll
+        for (int s = 0; s < MAX_SPLITS; ++s)
+          if (s < S) tt[u][s] = __ldcg(p + (int64_t)s * TILE_F4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < QG; ++u) {
+      const int q = q0 + u, col = (q * TPR + t) * 4;
+      if (!(active && col < C)) {
+        z4[q] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        continue;
+      }
+      float4 acc = tt[u][0];
+#pragma unroll
+      for (int s = 1; s < MAX_SPLITS; ++s)           // fixed split order: deterministic
+        if (s < S) { acc.x += tt[u][s].x; acc.y += tt[u][s].y; acc.z += tt[u][s].z; acc.w += tt[u][s].w; }
+      acc.x += b4[q].x; acc.y += b4[q].y; acc.z += b4[q].z; acc.w += b4[q].w;
+      const bool full = col + 4 <= C;
+      if (zrow) {
+        if (full && zvec) stg_stream4(zrow + col, acc);
+        else {
+          zrow[col] = acc.x;
+          if (col + 1 < C) zrow[col + 1] = acc.y;
+          if (col + 2 < C) zrow[col + 2] = acc.z;
+          if (col + 3 < C) zrow[col + 3] = acc.w;
+        }
+      }
+      if (!full) {                                   // ragged last group: columns >= C do not exist
+        if (col + 1 >= C) acc.y = -CUDART_INF_F;
+        if (col + 2 >= C) acc.z = -CUDART_INF_F;
+        acc.w = -CUDART_INF_F;
+      }
+      z4[q] = acc;
+    }
+  }
+}
 
 // dX = sum over splits of the parked partial tiles: U chunks of 256 float4 (8 rows of one tile) per pass.
 template <int U, int SMAX>
-__device__ __forceinline__ void reduce_dx(const Args& g, int* s_flag) {
+__device__ __forceinline__ void reduce_dx(const Args& g, const int* ctrs) {
   const int S = g.dx.splits;
   const int nchunks = g.dx.tiles_m * g.dx.tiles_n * 16;
   const int G = (int)gridDim.x;
   for (int c0 = blockIdx.x; c0 < nchunks; c0 += G * U) {
     if ((int)threadIdx.x < U) {
       const int c = c0 + (int)threadIdx.x * G;
-      if (c < nchunks) ptx::spin_until_ge(g.ctr + CTR_DX + (c >> 4), S);
+      if (c < nchunks) ptx::spin_until_ge(ctrs + CTR_DX + (c >> 4), S);
     }
     __syncthreads();
+    if (threadIdx.x == 0 && c0 == (int)blockIdx.x) stamp(g, 14);
     float4 t[U][SMAX];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -225,12 +270,11 @@ __device__ __forceinline__ void reduce_dx(const Args& g, int* s_flag) {
     }
     __syncthreads();
   }
-  (void)s_flag;
 }
 
 // TPR threads per loss row, NE logits per thread (C <= TPR * NE), 256 / TPR rows per CTA pass.
 template <int TPR, int NE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, HF_MIN_BLOCKS)
 head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmP,
                   const __grid_constant__ CUtensorMap tmDW, const __grid_constant__ Args g) {
@@ -248,6 +292,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) stamp(g, 0);
+  __shared__ volatile int s_last;                     // grid barrier: 0 = not known yet, 1 = not the last arriver, 2 = the last
+  if (threadIdx.x == 96) s_last = 0;                  // (ordered before every later use by the prologue's block barrier)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmX); ptx::prefetch_tensormap(&tmW); ptx::prefetch_tensormap(&tmDZ);
@@ -278,6 +324,11 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();                               // the previous launch of the stream (same workspace) is complete
   if (threadIdx.x == 0) stamp(g, 2);
+  const int parity = __ldcg(g.ctr) & 1;              // (stable until the last CTA passes the grid barrier)
+  int* const ctrs = g.ctr + CTR_SET0 + parity * CTR_SET_STRIDE;
+
+  constexpr int NQ = NE / 4;
+  constexpr int RPB = 256 / TPR;
 
   // ---- pipeline state.  Producer (thread 0): ring position of load #0 of the NEXT item to be (fully) issued, and
   // how many A / B parts of that item are already in flight.  MMA issuer (thread 32): its own ring position.
@@ -353,6 +404,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int i = 0; i < it.cnt; ++i) {
       ptx::mbar_wait(full_bar(m_stage), m_phase);
       ptx::tc_fence_after();
+      if (g.dbg && (i == 0 || i == it.cnt - 1)) stamp(g, (it.kind == 0 ? 17 : (it.kind == 1 ? 19 : 21)) + (i == 0 ? 0 : 1));
       const uint32_t sa = smem_base + m_stage * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
       for (int k = 0; k < TK / 16; ++k) {
@@ -377,6 +429,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     ptx::mbar_wait(tmem_full_bar, acc_parity);
     acc_parity ^= 1u;
     ptx::tc_fence_after();
+    if (threadIdx.x == 0 && it.kind != 0) stamp(g, 15);      // (last backward item: accumulator complete)
     const uint32_t rbase = wbase + (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
 #pragma unroll
@@ -404,8 +457,11 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ptx::tma_store_2d(&tmP, wbase, h * 64, it.part_row + q * 32);
         ptx::tma_store_2d(&tmP, wbase + 4096u, h * 64 + 32, it.part_row + q * 32);
         ptx::bulk_commit();
-        ptx::bulk_wait0();                           // the partial rows are WRITTEN (not merely read from smem) ...
-        asm volatile("fence.proxy.async;" ::: "memory");   // ... async-proxy writes ordered before the release below
+        // the partial rows are WRITTEN (not merely read out of shared memory) and visible to this thread, whose
+        // release (below, after the block barrier) then publishes them: no proxy fence on the writer's side (a
+        // generic `fence.proxy.async` is MEMBAR.ALL.GPU + an L1 invalidate in SASS)
+        ptx::bulk_wait0();
+        if (g.flags & 1) asm volatile("fence.proxy.async;" ::: "memory");
       }
     }
     if (it.do_db && h == 0) {                        // db of this class row: first of the 16 equal columns
@@ -417,13 +473,26 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     ptx::tc_fence_before();
     __syncthreads();                                 // accumulator + staging reusable; every warp's park is complete
     ptx::tc_fence_after();
-    if (it.kind != 2 && threadIdx.x == 0) ptx::red_release_add(g.ctr + it.ctr_idx, 1);
+    if (it.kind != 2 && threadIdx.x == 0) ptx::red_release_add(ctrs + it.ctr_idx, 1);
   };
 
   // ============================ phase F ============================
+  const int nF = my_items(g.f.items);
+  if (threadIdx.x == 0 && nF > 0) {
+    produce(decode_f(g, snake(0, g.f.items)), STAGES, true, true);
+    stamp(g, 16);
+  }
+  // The label-dependent scalars, IIF weights and bias of this CTA's FIRST loss-row block do not depend on the
+  // forward product: their (HBM-cold) loads are issued now -- after the operand requests of the first forward
+  // item, which must not queue behind the label -> class-weight dependency -- and land under phase F.
+  RowHead<TPR, NE> head0;
+  float4 bias0[NQ];
+  if ((int)blockIdx.x < g.row_blocks) {
+    row_head<TPR, NE, 0>(g.loss, blockIdx.x, head0);
+    load_bias<TPR, NE>(g, head0.active, bias0);
+  }
   {
-    const int n = my_items(g.f.items);
-    if (threadIdx.x == 0 && n > 0) produce(decode_f(g, snake(0, g.f.items)), STAGES, true, true);
+    const int n = nF;
     for (int k = 0; k < n; ++k) {
       const Item it = decode_f(g, snake(k, g.f.items));
       if (threadIdx.x == 0) {
@@ -446,7 +515,10 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int my_b = my_items(nB);
   bool b_issued = false;
   auto issue_b = [&]() {
-    if (threadIdx.x == 0 && !b_issued && my_b > 0) produce(decode_b(g, snake(0, nB)), STAGES, false, true);
+    if (threadIdx.x == 0 && !b_issued) {
+      stamp(g, 12);                                  // first loss row: loads returned, first reduction done
+      if (my_b > 0) produce(decode_b(g, snake(0, nB)), STAGES, false, true);
+    }
     b_issued = true;
   };
 
@@ -457,21 +529,28 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __shared__ RowSmem<256> row_sm;
     __shared__ float s_row_loss[256 / TPR];
     __shared__ int s_row_rank[256 / TPR];
-    constexpr int RPB = 256 / TPR;
-    PartialZ zl;
-    zl.part = g.part; zl.bias = g.bias; zl.z = const_cast<float*>(g.loss.z); zl.ldz = g.loss.ldz; zl.C = g.loss.C;
-    zl.tiles_n = g.f.tiles_n; zl.S = g.f.splits;
-    zl.zvec = (g.loss.ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(g.loss.z) & 15u) == 0;
     const int target = g.f.tiles_n * g.f.splits;
     for (int rb = blockIdx.x; rb < g.row_blocks; rb += gridDim.x) {
+      RowHead<TPR, NE> hd;
+      float4 b4[NQ], z4[NQ];
+      if (rb == (int)blockIdx.x) {
+        hd = head0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) b4[q] = bias0[q];
+      } else {
+        row_head<TPR, NE, 0>(g.loss, rb, hd);           // (in flight while thread 0 polls the m-tile's counter)
+        load_bias<TPR, NE>(g, hd.active, b4);
+      }
       if (threadIdx.x == 0) {
         const int mi = (rb * RPB) >> 7;               // the rows of one block share an m-tile (RPB divides 128)
-        ptx::spin_until_ge(g.ctr + CTR_READY_F + mi, target);
+        ptx::spin_until_ge(ctrs + CTR_READY_F + mi, target);
         if (rb == (int)blockIdx.x) stamp(g, 5);
       }
       __syncthreads();
+      load_logits<TPR, NE>(g, hd.row, hd.active, b4, z4);
       float my_loss; int cnt; bool active;
-      softmax_row_body_vec<TPR, NE, 0>(g.loss, rb, row_sm, my_loss, cnt, active, issue_b, zl);
+      row_tail<TPR, NE, 0>(g.loss, hd, z4, row_sm, my_loss, cnt, active, issue_b);
+      if (threadIdx.x == 0 && rb == (int)blockIdx.x) stamp(g, 13);
       const int t = threadIdx.x % TPR, lrow = threadIdx.x / TPR;
       if (t == 0) { s_row_loss[lrow] = active ? my_loss : 0.f; s_row_rank[lrow] = active ? cnt : 0x7fffffff; }
       __syncthreads();
@@ -484,23 +563,59 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
     issue_b();                                        // (a CTA without rows)
-    asm volatile("fence.proxy.async;" ::: "memory");  // our dZ stores (generic proxy) vs. the TMA reads to come
+    // dZ: generic-proxy stores here, async-proxy (TMA) reads in other CTAs.  The block barrier orders every
+    // thread's stores before thread 0's release; the READER fences the proxies after its acquire (phase B).
+    if (g.flags & 1) asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) {
-      stamp(g, 6);
-      ptx::red_release_add(g.ctr + CTR_ROWS, 1);
-    }
   }
 
-  // ============================ phase B ============================
+  // ============================ grid barrier + phase B ============================
   {
+    double* g_part = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(g.loss.scratch) + 16);
+    int* g_c1 = reinterpret_cast<int*>(g_part + gridDim.x);
+    int* g_c5 = g_c1 + gridDim.x;
     if (threadIdx.x == 0) {
+      stamp(g, 6);
+      __stcg(g_part + blockIdx.x, loss_part);         // this CTA's share of the loss / top-k counts: published by ...
+      __stcg(g_c1 + blockIdx.x, loss_c1);
+      __stcg(g_c5 + blockIdx.x, loss_c5);
+      // ... the barrier arrival (release: our rows of dZ and these partials; acquire: everybody else's, for the poll)
+      const int old = ptx::atom_add_acq_rel(ctrs + CTR_ROWS, 1);
+      __threadfence_block();
+      s_last = old == (int)gridDim.x - 1 ? 2 : 1;
       // grid barrier, producer thread only: every row of dZ is in L2 (the other threads go on to wait for the
       // accumulator of the first item)
-      ptx::spin_until_ge(g.ctr + CTR_ROWS, (int)gridDim.x);
+      ptx::spin_until_ge(ctrs + CTR_ROWS, (int)gridDim.x);
       asm volatile("fence.proxy.async;" ::: "memory");
       stamp(g, 7);
       if (my_b > 0) produce(decode_b(g, snake(0, nB)), STAGES, true, true);
+    }
+    if (warp == 3) {
+      // Duties of the LAST CTA to arrive (it knows every CTA's partials are published), done by an otherwise idle warp
+      // while the first backward item's operands are in flight: the deterministic loss sum / top-k counts (fixed
+      // lane-strided order + shuffle tree), zeroing the counter set of the NEXT launch, flipping the parity.
+      int last = 0;
+      if (lane == 0) { while ((last = s_last) == 0) { } }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last == 2) {
+        __threadfence_block();
+        double acc = 0.0;
+        int k1 = 0, k5 = 0;
+        for (unsigned i = lane; i < gridDim.x; i += 32) {
+          acc += __ldcg(g_part + i); k1 += __ldcg(g_c1 + i); k5 += __ldcg(g_c5 + i);
+        }
+        acc = warp_sum_d(acc); k1 = warp_sum_i(k1); k5 = warp_sum_i(k5);
+        if (lane == 0) {
+          if (g.loss.loss_sum) *g.loss.loss_sum = (float)acc;
+          if (g.loss.acc_counts) { g.loss.acc_counts[0] = k1; g.loss.acc_counts[1] = k5; }
+        }
+        int* other = g.ctr + CTR_SET0 + (parity ^ 1) * CTR_SET_STRIDE;
+        if (lane == 0) other[CTR_ROWS] = 0;
+        for (int i = lane; i < g.f.tiles_m; i += 32) other[CTR_READY_F + i] = 0;
+        const int ndx = g.dx.items > 0 ? g.dx.tiles_m * g.dx.tiles_n : 0;
+        for (int i = lane; i < ndx; i += 32) other[CTR_DX + i] = 0;
+        if (lane == 0) g.ctr[0] = parity ^ 1;
+      }
     }
     for (int k = 0; k < my_b; ++k) {
       const Item it = decode_b(g, snake(k, nB));
@@ -521,22 +636,11 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   // ============================ phase R ============================
   if (g.dx.items > 0) {
-    if (g.dx.splits <= 2) reduce_dx<4, 2>(g, nullptr);
-    else if (g.dx.splits <= 4) reduce_dx<2, 4>(g, nullptr);
-    else reduce_dx<1, 8>(g, nullptr);
+    if (g.dx.splits <= 2) reduce_dx<4, 2>(g, ctrs);
+    else if (g.dx.splits <= 4) reduce_dx<2, 4>(g, ctrs);
+    else reduce_dx<1, 8>(g, ctrs);
   }
-  if (threadIdx.x == 0) stamp(g, 10);
-
-  // ============================ tail ============================
-  // deterministic loss sum / top-k counts; the last CTA to take the ticket knows that every CTA is past all its
-  // waits and re-arms the counters for the next launch
-  if (grid_tail<256>(loss_part, loss_c1, loss_c5, g.loss.loss_sum, g.loss.acc_counts, g.loss.scratch)) {
-    if (threadIdx.x == 0) g.ctr[CTR_ROWS] = 0;
-    for (int i = threadIdx.x; i < g.f.tiles_m; i += 256) g.ctr[CTR_READY_F + i] = 0;
-    const int ndx = g.dx.items > 0 ? g.dx.tiles_m * g.dx.tiles_n : 0;
-    for (int i = threadIdx.x; i < ndx; i += 256) g.ctr[CTR_DX + i] = 0;
-  }
-  if (threadIdx.x == 0) stamp(g, 11);
+  if (threadIdx.x == 0) { stamp(g, 10); stamp(g, 11); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -589,6 +693,7 @@ static bool make_plan(int64_t B, int64_t D, int64_t C, bool need_dx, int sms, Pl
       const double cost = rounds * (per * 0.4 + 1.2) + 2.0 * items * 65536.0 / 10e6 + 0.05 * s;
       if (cost < best - 1e-9) { best = cost; best_s = s; }
     }
+    if (const char* e = getenv("IIF_B200_FUSED_SF")) { const int v = atoi(e); if (v >= 1 && v <= MAX_SPLITS && v <= pl.f.kb_total) best_s = v; }
     pl.f.splits = best_s; pl.f.items = tiles * best_s;
   }
   if (need_dx) {  // dX split, given the dW items it shares the phase with
@@ -604,6 +709,7 @@ static bool make_plan(int64_t B, int64_t D, int64_t C, bool need_dx, int sms, Pl
       const double cost = span * 0.4 + rounds * 1.2 + 2.0 * items * 65536.0 / 10e6 + 0.05 * s;
       if (cost < best - 1e-9) { best = cost; best_s = s; }
     }
+    if (const char* e = getenv("IIF_B200_FUSED_SDX")) { const int v = atoi(e); if (v >= 1 && v <= MAX_SPLITS && v <= pl.dx.kb_total) best_s = v; }
     pl.dx.splits = best_s; pl.dx.items = tiles * best_s;
     pl.b_dx_first = (pl.dx.kb_total + best_s - 1) / best_s >= pl.dw.kb_total;
   }
@@ -671,7 +777,7 @@ namespace iif {
 size_t head_fused_ws_bytes(int64_t B, int64_t D, int64_t C) {
   hf::Plan p;
   if (!hf::make_plan(B, D, C, true, kNumSMs, &p)) return 0;
-  return (size_t)16384 + p.part_bytes;
+  return (size_t)hf::WS_HEADER_BYTES + p.part_bytes;
 }
 
 // The whole step in one launch.  IIF_EUNSUPPORTED (nothing launched) when the shape / alignment does not qualify.
@@ -683,7 +789,7 @@ int head_fused_launch(const iif_head_args* h, void* stream, bool dry_run) {
   if (h->ldx % 8 || h->ldw % 8 || h->lddz % 8 || (h->lddw * 4) % 16 || !aligned16(h->x) || !aligned16(h->w) ||
       !aligned16(h->dz_bf16) || !aligned16(h->dw) || (h->iif && !aligned16(h->iif)) || (h->bias && !aligned16(h->bias)))
     return IIF_EUNSUPPORTED;
-  if (!h->scratch) return (h->loss_sum || h->acc_counts) ? IIF_EINVAL : IIF_EUNSUPPORTED;   // the tail's ticket lives there
+  if (!h->scratch) return (h->loss_sum || h->acc_counts) ? IIF_EINVAL : IIF_EUNSUPPORTED;   // the CTAs' loss partials live there
   if (h->acc_counts && !h->rank) return IIF_EINVAL;
   // the ragged last float4 group of a row writes its dZ padding columns: the row pitch must hold them
   if (h->lddz < (C + 3) / 4 * 4) return IIF_EUNSUPPORTED;
@@ -691,7 +797,7 @@ int head_fused_launch(const iif_head_args* h, void* stream, bool dry_run) {
   if (sms <= 0) { cudaGetLastError(); return IIF_EDRIVER; }
   hf::Plan p;
   if (!hf::make_plan(B, D, C, h->dx != nullptr, sms, &p)) return IIF_EUNSUPPORTED;
-  const size_t need = (size_t)16384 + p.part_bytes;
+  const size_t need = (size_t)hf::WS_HEADER_BYTES + p.part_bytes;
   if (!h->ws || h->ws_bytes < need || !aligned16(h->ws)) return IIF_EUNSUPPORTED;
   if (dry_run) return IIF_OK;
 
@@ -699,7 +805,7 @@ int head_fused_launch(const iif_head_args* h, void* stream, bool dry_run) {
   g.f = p.f; g.dx = p.dx; g.dw = p.dw; g.b_dx_first = p.b_dx_first; g.row_blocks = p.row_blocks;
   uint8_t* ws = reinterpret_cast<uint8_t*>(h->ws);
   g.ctr = reinterpret_cast<int*>(ws + hf::CTR_BYTE_OFFSET);
-  g.part = reinterpret_cast<float4*>(ws + 16384);
+  g.part = reinterpret_cast<float4*>(ws + hf::WS_HEADER_BYTES);
   g.bias = h->bias;
   make_ce_row_args(g.loss, h->z, h->ldz, h->iif, h->label, h->class_weight, h->sample_weight, h->ignore_index, h->scale,
                    B, C, h->loss_i, h->loss_sum, nullptr, 0, h->dz_bf16, h->lddz, nullptr, h->argmax, h->rank,
@@ -707,6 +813,10 @@ int head_fused_launch(const iif_head_args* h, void* stream, bool dry_run) {
   g.dx_out = h->dx; g.dx_bf16 = h->dx_dtype == IIF_DTYPE_BF16; g.lddx = h->lddx;
   g.db = h->db;
   g.dbg = hf::g_dbg;
+  {
+    static const int flags = [] { const char* e = getenv("IIF_B200_FUSED_FLAGS"); return e ? atoi(e) : 0; }();
+    g.flags = flags;
+  }
   CUtensorMap mx, mw, mdz, mp, mdw;
   int rc;
   if ((rc = make_map(&mx, h->x, false, (uint64_t)D, (uint64_t)B, (uint64_t)h->ldx, 64, 64))) return rc;

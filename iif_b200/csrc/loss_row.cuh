@@ -139,75 +139,119 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2: 2 ulp, exp2
 // out-of-row elements are encoded as z = -inf, s = 1 (so no per-element bounds logic survives the loads),
 // the label's column is found with one range test per float4, optional outputs (argmax / rank) sit behind
 // warp-uniform branches, exp is one FMUL + MUFU.EX2 on (a - max) * log2(e).
+// The label-dependent scalars and the IIF weights of one row: everything the row needs that does NOT depend on the
+// logits.  Split from the rest of the body so that a caller whose logits arrive late (the one-launch head step waits
+// for the forward GEMM's partial tiles) can have these loads in flight while it waits.
+template <int TPR, int NE>
+struct RowHead {
+  static constexpr int NQ = NE / 4;
+  static constexpr bool CACHE_S = NE <= 8;   // wider rows re-read the IIF weights (L1) instead of holding them
+  int64_t row; bool active, y_ok, dual; int yi, ybi; float g, gb;
+  float4 s4[CACHE_S ? NQ : 1];
+};
+
+template <int TPR>
+__device__ __forceinline__ float4 row_load_s(const RowArgs& a, int q, int t, bool active) {
+  const int col = (q * TPR + t) * 4, C = a.C;
+  if (!(a.iif && active && col < C)) return make_float4(1.f, 1.f, 1.f, 1.f);
+  if (col + 4 <= C) return __ldg(reinterpret_cast<const float4*>(a.iif + col));
+  // ragged last group (C % 4 != 0: only reachable through a ZLoad functor): no read past the vector's end
+  return make_float4(__ldg(a.iif + col), col + 1 < C ? __ldg(a.iif + col + 1) : 1.f, col + 2 < C ? __ldg(a.iif + col + 2) : 1.f, 1.f);
+}
+
+template <int TPR, int NE, int MODE>
+__device__ __forceinline__ void row_head(const RowArgs& a, int64_t row_block, RowHead<TPR, NE>& h) {
+  constexpr int THREADS = TPR > 256 ? TPR : 256;
+  const int t = threadIdx.x % TPR;
+  const int lrow = threadIdx.x / TPR;
+  h.row = row_block * (THREADS / TPR) + lrow;
+  h.active = h.row < a.B;
+  const int C = a.C;
+  int64_t y = -1;
+  if (h.active && a.label) y = __ldg(a.label + h.row);
+  const bool y_in = h.active && y >= 0 && y < C;
+  h.y_ok = y_in && y != a.ignore_index;
+  h.yi = y_in ? (int)y : -1;
+  h.g = 0.f;
+  if (MODE == 0 && h.y_ok) {
+    h.g = a.scale;
+    if (a.cw) h.g *= __ldg(a.cw + y);
+    if (a.sw) h.g *= __ldg(a.sw + h.row);
+  }
+  // second label of a Mixup pair (cls/custom.py:116-117): same rules, weight (1 - lam); the first gets lam
+  h.dual = MODE == 0 && a.label_b != nullptr;
+  h.ybi = -1;
+  h.gb = 0.f;
+  if (h.dual) {
+    const int64_t yb = h.active ? __ldg(a.label_b + h.row) : -1;
+    const bool yb_in = h.active && yb >= 0 && yb < C;
+    h.ybi = yb_in ? (int)yb : -1;
+    if (yb_in && yb != a.ignore_index) {
+      h.gb = a.scale * (1.f - a.lam);
+      if (a.cw) h.gb *= __ldg(a.cw + yb);
+      if (a.sw) h.gb *= __ldg(a.sw + h.row);
+    }
+    h.g *= a.lam;
+  }
+  if constexpr (RowHead<TPR, NE>::CACHE_S) {
+#pragma unroll
+    for (int q = 0; q < NE / 4; ++q) h.s4[q] = row_load_s<TPR>(a, q, t, h.active);
+  }
+}
+
+template <int TPR, int NE, int MODE, class Hook>
+__device__ __forceinline__ void row_tail(const RowArgs& a, const RowHead<TPR, NE>& h, float4 (&z4)[NE / 4],
+                                         RowSmem<(TPR > 256 ? TPR : 256)>& sm, float& my_loss_out, int& cnt_out,
+                                         bool& active_out, Hook hook);
+
 template <int TPR, int NE, int MODE, class Hook, class ZLoad = NoZLoad>
 __device__ __forceinline__ void softmax_row_body_vec(const RowArgs& a, int64_t row_block,
                                                      RowSmem<(TPR > 256 ? TPR : 256)>& sm, float& my_loss_out,
                                                      int& cnt_out, bool& active_out, Hook hook, ZLoad zload = ZLoad()) {
-  constexpr int THREADS = TPR > 256 ? TPR : 256;
-  constexpr int WPR = TPR / 32;
   constexpr int NQ = NE / 4;
-  constexpr bool CACHE_S = NE <= 8;          // wider rows re-read the IIF weights (L1) instead of holding them
-  constexpr float L2E = 1.4426950408889634f;
-  auto& s_f = sm.f;
-  auto& s_i = sm.i;
+  RowHead<TPR, NE> h;
+  row_head<TPR, NE, MODE>(a, row_block, h);
   const int t = threadIdx.x % TPR;
-  const int lrow = threadIdx.x / TPR;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w0 = (warp / WPR) * WPR;
-  const int64_t row = row_block * (THREADS / TPR) + lrow;
-  const bool active = row < a.B;
   const int C = a.C;
-  const float* zr = a.z + (active ? row : 0) * a.ldz;
-  const bool want_rank = a.rank != nullptr, want_arg = a.argmax != nullptr;
-  const bool raw_only = (MODE == 1 && !a.softmax);      // activation mode without softmax: out = z * iif
-
-  int64_t y = -1;
-  if (active && a.label) y = __ldg(a.label + row);
-  const bool y_in = active && y >= 0 && y < C;
-  const bool y_ok = y_in && y != a.ignore_index;
-  const int yi = y_in ? (int)y : -1;
-  float g = 0.f;
-  if (MODE == 0 && y_ok) {
-    g = a.scale;
-    if (a.cw) g *= __ldg(a.cw + y);
-    if (a.sw) g *= __ldg(a.sw + row);
-  }
-  // second label of a Mixup pair (cls/custom.py:116-117): same rules, weight (1 - lam); the first gets lam
-  const bool dual = MODE == 0 && a.label_b != nullptr;
-  int ybi = -1;
-  float gb = 0.f;
-  if (dual) {
-    const int64_t yb = active ? __ldg(a.label_b + row) : -1;
-    const bool yb_in = active && yb >= 0 && yb < C;
-    ybi = yb_in ? (int)yb : -1;
-    if (yb_in && yb != a.ignore_index) {
-      gb = a.scale * (1.f - a.lam);
-      if (a.cw) gb *= __ldg(a.cw + yb);
-      if (a.sw) gb *= __ldg(a.sw + row);
-    }
-    g *= a.lam;
-  }
-
-  // ---- loads
-  float4 z4[NQ], s4[CACHE_S ? NQ : 1];
-  auto load_s = [&](int q) -> float4 {
-    const int col = (q * TPR + t) * 4;
-    if (!(a.iif && active && col < C)) return make_float4(1.f, 1.f, 1.f, 1.f);
-    if (col + 4 <= C) return __ldg(reinterpret_cast<const float4*>(a.iif + col));
-    // ragged last group (C % 4 != 0: only reachable through a ZLoad functor): no read past the vector's end
-    return make_float4(__ldg(a.iif + col), col + 1 < C ? __ldg(a.iif + col + 1) : 1.f, col + 2 < C ? __ldg(a.iif + col + 2) : 1.f, 1.f);
-  };
+  const float* zr = a.z + (h.active ? h.row : 0) * a.ldz;
+  float4 z4[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int col = (q * TPR + t) * 4;
     if constexpr (std::is_same<ZLoad, NoZLoad>::value)
-      z4[q] = (active && col < C) ? ldg_stream4(zr + col)
-                                  : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+      z4[q] = (h.active && col < C) ? ldg_stream4(zr + col)
+                                    : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
     else
-      z4[q] = (active && col < C) ? zload(col, row)
-                                  : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-    if constexpr (CACHE_S) s4[q] = load_s(q);
+      z4[q] = (h.active && col < C) ? zload(col, h.row)
+                                    : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
   }
+  row_tail<TPR, NE, MODE>(a, h, z4, sm, my_loss_out, cnt_out, active_out, hook);
+}
+
+// Lean 128-bit path of the rows, continued: everything after the loads.
+template <int TPR, int NE, int MODE, class Hook>
+__device__ __forceinline__ void row_tail(const RowArgs& a, const RowHead<TPR, NE>& h, float4 (&z4)[NE / 4],
+                                         RowSmem<(TPR > 256 ? TPR : 256)>& sm, float& my_loss_out, int& cnt_out,
+                                         bool& active_out, Hook hook) {
+  constexpr int WPR = TPR / 32;
+  constexpr int NQ = NE / 4;
+  constexpr bool CACHE_S = RowHead<TPR, NE>::CACHE_S;
+  constexpr float L2E = 1.4426950408889634f;
+  auto& s_f = sm.f;
+  auto& s_i = sm.i;
+  const int t = threadIdx.x % TPR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w0 = (warp / WPR) * WPR;
+  const int64_t row = h.row;
+  const bool active = h.active;
+  const int C = a.C;
+  const bool want_rank = a.rank != nullptr, want_arg = a.argmax != nullptr;
+  const bool raw_only = (MODE == 1 && !a.softmax);      // activation mode without softmax: out = z * iif
+  const bool y_ok = h.y_ok, dual = h.dual;
+  const int yi = h.yi, ybi = h.ybi;
+  const float g = h.g, gb = h.gb;
+  auto load_s = [&](int q) -> float4 { return row_load_s<TPR>(a, q, t, active); };
+  const float4* s4 = h.s4;
 
   // Register diet (the row loop of a big batch lives on occupancy): only the raw logits (later overwritten
   // by their exponentials) and, for narrow rows, the IIF weights stay in registers; z * s is one FMUL

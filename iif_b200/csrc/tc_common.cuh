@@ -87,13 +87,17 @@ inline cudaError_t launch_cooperative(cudaLaunchConfig_t& cfg, const void* fn, v
     ok = (e && e[0] == '0') ? 0 : 1;
     pdl_ok.store(ok, std::memory_order_relaxed);
   }
+  // IIF_B200_COOP=0 (experiments only): plain launch -- co-residency is then the caller's problem
+  static const bool coop = [] { const char* e = getenv("IIF_B200_COOP"); return !(e && e[0] == '0'); }();
   cudaError_t e = cudaSuccess;
   for (int attempt = 0; attempt < 2; ++attempt) {
     cudaLaunchAttribute attrs[2];
     int na = 0;
-    attrs[na].id = cudaLaunchAttributeCooperative;
-    attrs[na].val.cooperative = 1;
-    ++na;
+    if (coop) {
+      attrs[na].id = cudaLaunchAttributeCooperative;
+      attrs[na].val.cooperative = 1;
+      ++na;
+    }
     const bool pdl = want_pdl && pdl_ok.load(std::memory_order_relaxed) == 1;
     if (pdl) {
       attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -103,7 +107,7 @@ inline cudaError_t launch_cooperative(cudaLaunchConfig_t& cfg, const void* fn, v
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     e = cudaLaunchKernelExC(&cfg, fn, kargs);
-    if (e == cudaSuccess || !pdl) break;
+    if (e == cudaSuccess || !pdl || !coop) break;
     cudaGetLastError();                      // rejected together: keep the co-residency guarantee, drop the overlap
     pdl_ok.store(0, std::memory_order_relaxed);
   }

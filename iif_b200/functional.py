@@ -82,6 +82,33 @@ def sigmoid_bce(pred, target, *, pos_weight=None, col_weight=None, sample_weight
                              "sum" if reduce else "elem", gamma, alpha)
 
 
+class _SigmoidBCEDense(torch.autograd.Function):
+    """Sigmoid BCE against already-expanded (dense / soft) targets [B,C] with element / row weights
+    (mmdet cross_entropy_loss.py:100-106, the pred.dim() == label.dim() branch)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, pos_weight, weight, scale, mode):
+        need = ctx.needs_input_grad[0]
+        r = ops.sigmoid_bce_dense(_f32(pred), _f32(target), pos_weight=pos_weight, weight=weight, scale=scale,
+                                  want_elem=(mode == "elem"), want_dz=need, want_sum=(mode == "sum"))
+        ctx.in_dtype, ctx.mode = pred.dtype, mode
+        if need:
+            ctx.save_for_backward(r["dz_f32"])
+        return r["loss_sum"] if mode == "sum" else r["loss_elem"]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dz,) = ctx.saved_tensors
+        out = (ops.scale_rows(dz, g) if dz.numel() else dz) if ctx.mode == "sum" else dz * g
+        if ctx.in_dtype != torch.float32:
+            out = out.to(ctx.in_dtype)
+        return out, None, None, None, None, None
+
+
+def sigmoid_bce_dense(pred, target, *, pos_weight=None, weight=None, scale=1.0, reduce=True):
+    return _SigmoidBCEDense.apply(pred, target, pos_weight, weight, scale, "sum" if reduce else "elem")
+
+
 class _NormalizeRows(torch.autograd.Function):
     """y_i = pre_i r(|pre_i x_i|) x_i -- the operand normalisation of the normalised classifiers
     (mmdet normed_predictor.py:36-40,70-76; cls/resnet_cifar.py:66-71) with its exact backward

@@ -95,13 +95,14 @@ def cross_entropy(pred, label, weight=None, reduction="mean", avg_factor=None, c
 
 def binary_cross_entropy(pred, label, weight=None, reduction="mean", avg_factor=None, class_weight=None,
                          ignore_index=-100, loss_weight=1.0):
-    """cross_entropy_loss.py:74-111 for class-index labels (pred.dim() != label.dim())."""
+    """cross_entropy_loss.py:74-111: class-index labels [B] (pred.dim() != label.dim(): the one-hot expansion of
+    :53-71 happens inside the kernel) or already-expanded labels [B,C] (:100-103 skipped, `weight` element-wise)."""
     ignore_index = -100 if ignore_index is None else ignore_index
-    if pred.dim() == label.dim():
-        raise NotImplementedError("iif_b200 sigmoid BCE takes class-index labels [B] (the loss_cls call path)")
     if pred.size(0) == 0:
         return loss_weight * _empty_result(pred, reduction, avg_factor)
     scale, reduce = _resolve(reduction, avg_factor, loss_weight, pred.numel())
+    if pred.dim() == label.dim():
+        return F_.sigmoid_bce_dense(pred, label, pos_weight=class_weight, weight=weight, scale=scale, reduce=reduce)
     return F_.sigmoid_bce(pred, label, pos_weight=class_weight,
                           sample_weight=None if weight is None else weight.float(), ignore_index=ignore_index,
                           scale=scale, reduce=reduce)
@@ -241,11 +242,11 @@ class FasaIIFLoss(nn.Module):
         loss_cls = self.cls_criterion(cls_score, label, weight, class_weight=class_weight, reduction=reduction,
                                       avg_factor=avg_factor, **kwargs)
         if self.use_cums:
-            # :154-160 without the python loop over label.unique() and its .item() syncs
-            lab = label.clamp(0, self.num_classes)
+            # :154-160 without the python loop over label.unique() and its .item() syncs: one segmented-sum kernel
+            # (a [B,C] sigmoid loss contributes its row sums, negative labels index from the end like the
+            # reference's cum[int(u_l)])
             with torch.no_grad():
-                self.cum_labels.index_add_(0, lab, torch.ones_like(lab, dtype=self.cum_labels.dtype))
-                self.cum_losses.index_add_(0, lab, loss_cls.detach().to(self.cum_losses.dtype))
+                ops.class_accumulate(label, loss_cls.detach().float(), self.cum_losses, self.cum_labels)
             loss_cls = loss_cls.mean()
         return loss_cls
 
@@ -274,12 +275,18 @@ class Linear(nn.Linear):
         self._w16_key = None
 
     def weight_bf16(self):
+        """bf16 operand copy of the fp32 master weight.  Refreshed on EVERY training forward (one small cast kernel):
+        optimizers, EMA hooks and fp16 master-copy hooks write through `.data`, which does not bump `_version`.  In
+        eval mode the copy is kept while (version, storage) are unchanged; `invalidate()` drops it explicitly."""
         key = (self.weight._version, self.weight.data_ptr())
-        if self._w16 is None or self._w16_key != key:
+        if self.training or self._w16 is None or self._w16_key != key:
             with torch.no_grad():
                 self._w16 = ops.scale_rows(self.weight.detach().float(), None, bf16=True)
             self._w16_key = key
         return self._w16
+
+    def invalidate(self):
+        self._w16 = None
 
     def forward(self, x):
         if self.compute == "bf16":

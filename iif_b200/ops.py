@@ -233,6 +233,110 @@ def sigmoid_bce(z, label, *, pos_weight=None, col_weight=None, sample_weight=Non
     return r
 
 
+def sigmoid_bce_dense(z, target, *, pos_weight=None, weight=None, scale=1.0, want_elem=False, want_dz=True,
+                      want_sum=True):
+    """Sigmoid BCE with already-expanded (dense / soft) targets [B,C]; `weight`: None, [B], [B,1] or [B,C]."""
+    z = _rows(z, "z", torch.float32)
+    B, Cc = z.shape
+    dev = z.device
+    target = _rows(target, "target", torch.float32)
+    if tuple(target.shape) != (B, Cc):
+        raise ValueError(f"iif_b200: dense BCE target must be [{B},{Cc}], got {tuple(target.shape)}")
+    pw = _vec(pos_weight, "pos_weight", Cc)
+    ldw = 0
+    if weight is not None:
+        _cuda(weight, "weight")
+        weight = weight.float()
+        if weight.numel() == B:
+            weight = weight.reshape(-1).contiguous()
+        elif tuple(weight.shape) == (B, Cc):
+            weight = _rows(weight, "weight", torch.float32)
+            ldw = _ld(weight)
+        else:
+            raise ValueError(f"iif_b200: dense BCE weight must have {B} or {B}x{Cc} elements")
+    r = dict(loss_i=torch.empty(B, dtype=torch.float32, device=dev))
+    r["loss_sum"] = torch.zeros((), dtype=torch.float32, device=dev) if want_sum else None
+    r["loss_elem"] = torch.empty(B, Cc, dtype=torch.float32, device=dev) if want_elem else None
+    r["dz_f32"] = torch.empty(B, Cc, dtype=torch.float32, device=dev) if want_dz else None
+    if B == 0:
+        return r
+    _lib.check(_lib.load().iif_sigmoid_bce_dense_fwd_bwd(
+        _ptr(z), _ld(z), _ptr(target), _ld(target), _ptr(pw), _ptr(weight), ldw, float(scale), B, Cc,
+        _ptr(r["loss_elem"]), Cc, _ptr(r["loss_i"]), _ptr(r["loss_sum"]), _ptr(r["dz_f32"]), Cc,
+        _ptr(loss_scratch(dev, B)), _stream(dev)), "sigmoid_bce_dense_fwd_bwd")
+    return r
+
+
+def class_accumulate(label, loss, cum_losses, cum_labels):
+    """cum_labels[c] += #{label == c}; cum_losses[c] += sum of loss rows with label c (fasa_iif_loss.py:154-160).
+    In place on the two fp32 accumulators [num_bins]; `loss` is [B] or [B,C] (rows are summed)."""
+    label = _vec(label, "label", label.numel(), torch.int64)
+    B = label.numel()
+    _cuda(loss, "loss", torch.float32)
+    if loss.dim() == 1:
+        loss2 = loss.contiguous().reshape(B, 1) if B else loss.reshape(0, 1)
+    else:
+        loss2 = _rows(loss.reshape(B, -1), "loss", torch.float32)
+    _cuda(cum_losses, "cum_losses", torch.float32)
+    _cuda(cum_labels, "cum_labels", torch.float32)
+    nb = cum_losses.numel()
+    if cum_labels.numel() != nb or not cum_losses.is_contiguous() or not cum_labels.is_contiguous():
+        raise ValueError("iif_b200: cum_losses / cum_labels must be contiguous and of equal length")
+    if B:
+        _lib.check(_lib.load().iif_class_accumulate(_ptr(label), _ptr(loss2), _ld(loss2) if loss2.shape[1] > 1 else 1,
+                                                    int(loss2.shape[1]), B, nb, _ptr(cum_losses), _ptr(cum_labels),
+                                                    _stream(label.device)), "class_accumulate")
+
+
+_STATS_WS = {}
+
+
+def class_feature_stats(x, label, feature_mean, feature_var, feature_used, decay):
+    """FasaBBoxHead.fa_update (fasa_bbox_head.py:118-148) for all classes present in `label`, in place on the running
+    statistics feature_mean / feature_var [num_bins, D] and feature_used [num_bins] (fp32)."""
+    x = _rows(x, "x", torch.float32)
+    B, D = x.shape
+    label = _vec(label, "label", B, torch.int64)
+    for t, n in ((feature_mean, "feature_mean"), (feature_var, "feature_var")):
+        _cuda(t, n, torch.float32)
+        if t.dim() != 2 or t.shape[1] != D or t.stride(1) != 1:
+            raise ValueError(f"iif_b200: {n} must be [num_bins,{D}] with unit inner stride")
+    nb = feature_mean.shape[0]
+    _cuda(feature_used, "feature_used", torch.float32)
+    if feature_var.shape[0] != nb or feature_used.numel() != nb or feature_mean.stride(0) != feature_var.stride(0):
+        raise ValueError("iif_b200: feature_mean / feature_var / feature_used disagree")
+    key = (x.device.index, nb)
+    ws = _STATS_WS.get(key)
+    if ws is None:
+        ws = _STATS_WS[key] = torch.zeros(nb, dtype=torch.int32, device=x.device)
+    if B:
+        _lib.check(_lib.load().iif_class_feature_stats(_ptr(x), _ld(x), _ptr(label), B, D, nb, float(decay),
+                                                       _ptr(feature_mean), _ptr(feature_var), int(feature_mean.stride(0)),
+                                                       _ptr(feature_used), _ptr(ws), _stream(x.device)),
+                   "class_feature_stats")
+
+
+def shot_accuracy(preds, labels, train_counts, many_shot_thr=100, low_shot_thr=20, want_class_acc=False):
+    """many / median / low-shot accuracy (cls/per_shot_acc.py:62-105).  preds int32/int64 [n], labels int64 [n],
+    train_counts int64 [C] (per-class TRAIN counts).  Returns (out3 float64 [3] on the device, test_counts,
+    correct_counts[, class_acc float64 [C], -1 where the class is absent from `labels`])."""
+    _cuda(preds, "preds")
+    n = preds.numel()
+    preds = preds.reshape(-1).to(torch.int32).contiguous()
+    labels = _vec(labels, "labels", n, torch.int64)
+    train_counts = _vec(train_counts, "train_counts", train_counts.numel(), torch.int64)
+    Cc = train_counts.numel()
+    dev = preds.device
+    test = torch.empty(Cc, dtype=torch.int64, device=dev)
+    correct = torch.empty(Cc, dtype=torch.int64, device=dev)
+    out3 = torch.empty(3, dtype=torch.float64, device=dev)
+    cacc = torch.empty(Cc, dtype=torch.float64, device=dev) if want_class_acc else None
+    _lib.check(_lib.load().iif_shot_accuracy(_ptr(preds), _ptr(labels), n, _ptr(train_counts), Cc, int(many_shot_thr),
+                                             int(low_shot_thr), _ptr(test), _ptr(correct), _ptr(out3), _ptr(cacc),
+                                             _stream(dev)), "shot_accuracy")
+    return (out3, test, correct, cacc) if want_class_acc else (out3, test, correct)
+
+
 def scale_rows(x, g=None, *, bf16=False, pad_ld=False):
     """x[rows, cols] fp32 * g (None | 0-dim device scalar | [rows]) -> fp32 or bf16 (optionally ld padded to 8)."""
     x = _rows(x, "x", torch.float32)

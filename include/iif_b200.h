@@ -173,6 +173,45 @@ IIF_API int iif_sigmoid_focal_fwd_bwd(const float* z, int64_t ldz, const int64_t
                               float* loss_sum, float* dz_f32, int64_t lddz_f32, void* dz_bf16,
                               int64_t lddz_bf16, int32_t* scratch, void* stream);
 
+/* Sigmoid BCE with ALREADY-EXPANDED labels: `target` is a dense [B,C] fp32 matrix of (soft) targets in [0,1] -- the
+ * branch binary_cross_entropy takes when pred.dim() == label.dim(), seg/mmdet/models/losses/cross_entropy_loss.py:100-106.
+ *   e = (1 - t) z + (1 + (pw - 1) t) softplus(-z);  loss_elem = scale * w * e;  dz = scale * w * d e / d z
+ * `weight`: element weights [B,C] (ldw >= C), a per-row vector [B] (ldw == 0), or NULL.  loss_i = row sums. */
+IIF_API int iif_sigmoid_bce_dense_fwd_bwd(const float* z, int64_t ldz, const float* target, int64_t ldt,
+                                  const float* pos_weight, const float* weight, int64_t ldw, float scale,
+                                  int64_t B, int64_t C, float* loss_elem, int64_t ldl, float* loss_i,
+                                  float* loss_sum, float* dz_f32, int64_t lddz, int32_t* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FASA bookkeeping around loss_cls and the many / median / low-shot accuracy (8f-2)
+ * ------------------------------------------------------------------------------------------- */
+
+/* cum_labels[c] += #{i : label_i == c};  cum_losses[c] += sum_{i : label_i == c} rowsum(loss_i)  -- the python loop over
+ * label.unique() with its .item() syncs at seg/mmdet/models/losses/fasa_iif_loss.py:154-160.  `loss` is [B] (loss_cols
+ * = 1) or [B, loss_cols] (sigmoid mode: the reference sums the row).  A negative label indexes from the end like the
+ * reference's python indexing; labels outside [-num_bins, num_bins) (where the reference raises IndexError) are skipped.
+ * Deterministic (one warp per class, fixed-order sums). */
+IIF_API int iif_class_accumulate(const int64_t* label, const float* loss, int64_t ldl, int64_t loss_cols, int64_t B,
+                         int64_t num_bins, float* cum_losses, float* cum_labels, void* stream);
+
+/* FasaBBoxHead.fa_update / fa_update_push (seg/mmdet/models/roi_heads/bbox_heads/fasa_bbox_head.py:118-148): for every
+ * class c present in `label`, mean and variance (unbiased for n > 1) of the class's feature rows, folded into the running
+ * statistics: first sighting (feature_used[c] == 0) stores them and bumps feature_used[c], later ones blend with
+ * `decay` (decay * new + (1 - decay) * old).  x [B,D] fp32; feature_mean / feature_var [num_bins, D] (ldm); B <= 8192.
+ * `ws_zeroed`: iif_class_feature_stats_ws_bytes(num_bins) bytes, zero on entry (left zero on exit). */
+IIF_API int iif_class_feature_stats(const float* x, int64_t ldx, const int64_t* label, int64_t B, int64_t D,
+                            int64_t num_bins, float decay, float* feature_mean, float* feature_var, int64_t ldm,
+                            float* feature_used, int32_t* ws_zeroed, void* stream);
+IIF_API size_t iif_class_feature_stats_ws_bytes(int64_t num_bins);
+
+/* shot_acc (cls/per_shot_acc.py:62-105): per-class test / correct counts of (preds, labels) -- integer, bit-exact --
+ * and the mean class accuracy over the classes PRESENT in `labels` whose TRAIN count is > many_shot_thr (out3[0]),
+ * < low_shot_thr (out3[2]) or in between (out3[1]); 0 for an empty group.  class_acc [C] (optional): correct / test,
+ * -1 for classes absent from `labels`.  preds int32 (the argmax output of the loss rows), labels int64. */
+IIF_API int iif_shot_accuracy(const int32_t* preds, const int64_t* labels, int64_t n, const int64_t* train_counts,
+                      int64_t C, int64_t many_shot_thr, int64_t low_shot_thr, int64_t* test_counts,
+                      int64_t* correct_counts, double* out3, double* class_acc, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * small elementwise helpers on [rows, cols] matrices
  * ------------------------------------------------------------------------------------------- */
@@ -257,7 +296,7 @@ IIF_API int iif_linear_bwd_bf16(const void* dz, int64_t lddz, const void* x, int
  * it off.  iif_debug_capacity: resident-CTA capacity of the current device for the tensor-core kernel
  * (the split-K rendezvous is only enabled for grids that fit it). */
 IIF_API void iif_debug_timing(long long* buf);
-IIF_API void iif_debug_timing_fused(long long* buf);       /* one-launch step: 16 int64 per CTA, see tools/tc_timing.py */
+IIF_API void iif_debug_timing_fused(long long* buf);       /* one-launch step: 32 int64 per CTA, see tools/fused_timing.py */
 IIF_API int iif_debug_fused_plan(int64_t B, int64_t D, int64_t C, int need_dx, int sms, int* out12);   /* host only: the one-launch step's plan */
 IIF_API void iif_debug_timing_allreduce(long long* buf);   /* 8 int64 per CTA: start, after handshake, after data, end */
 IIF_API int iif_debug_capacity(int* detail6 /* host, optional: occupancy API, by smem, by regs, regs, smem/SM, static smem */);

@@ -322,6 +322,74 @@ def cosnorm_classifier(x, w, gz, scale=16.0):
     return z, _norm_rows_bwd(x, gz @ ew, ax, cx), _norm_rows_bwd(w, gz.T @ ex, aw, cw)
 
 
+def cls_normed_linear(x, w_in_out, gz):
+    """classification NormedLinear (cls/resnet_cifar.py:38-48): out = F.normalize(x, dim=1) @ F.normalize(W, dim=0),
+    W stored [in, out] (F.normalize: v / max(|v|, 1e-12)).  Returns z, dx, dw ([in, out] like the parameter)."""
+    wt = np.asarray(w_in_out, np.float64).T                  # [out, in]: columns of W are rows here
+    ex, ax, cx = _norm_rows(x, None, "unit", 1.0, 1.0, 1e-12)
+    ew, aw, cw = _norm_rows(wt, None, "unit", 1.0, 1.0, 1e-12)
+    z = ex @ ew.T
+    gz = np.asarray(gz, np.float64)
+    return z, _norm_rows_bwd(x, gz @ ew, ax, cx), _norm_rows_bwd(wt, gz.T @ ex, aw, cw).T
+
+
+def cosnorm_classifier_lr(x, w, gz, scale):
+    """CosNorm_Classifier(lr_scale=True) (cls/resnet_cifar.py:56-57,75-76): z = scale^2 (x/(1+|x|)) (w/|w|)^T with a
+    learnable scalar.  Returns z, dx, dw, dscale."""
+    s2 = float(np.asarray(scale).reshape(-1)[0]) ** 2
+    z0, dx0, dw0 = cosnorm_classifier(x, w, np.asarray(gz, np.float64) * s2, scale=1.0)
+    dscale = 2.0 * float(np.asarray(scale).reshape(-1)[0]) * float((np.asarray(gz, np.float64) * z0).sum())
+    return z0 * s2, dx0, dw0, dscale
+
+
+# ----------------------------------------------------------------------------------------
+# 8f-4  FASA bookkeeping
+# ----------------------------------------------------------------------------------------
+def class_accumulate(label, loss, num_bins, cum_losses=None, cum_labels=None):
+    """fasa_iif_loss.py:154-160: for u in label.unique(): cum_labels[int(u)] += #rows, cum_losses[int(u)] +=
+    loss[rows].sum() -- python indexing, so a negative label counts from the end; [B,C] losses sum their rows."""
+    y = np.asarray(label, np.int64).reshape(-1)
+    l = np.asarray(loss, np.float64).reshape(y.shape[0], -1).sum(1)
+    cl = np.zeros(num_bins) if cum_losses is None else np.array(cum_losses, np.float64)
+    cn = np.zeros(num_bins) if cum_labels is None else np.array(cum_labels, np.float64)
+    for u in np.unique(y):
+        m = y == u
+        cn[int(u)] += m.sum()
+        cl[int(u)] += l[m].sum()
+    return cl, cn
+
+
+def class_feature_stats(x, label, mean, var, used, decay):
+    """ConvFCFASABBoxHead.fa_update / fa_update_push (fasa_bbox_head.py:118-148); returns the updated copies."""
+    x = np.asarray(x, np.float64)
+    y = np.asarray(label, np.int64).reshape(-1)
+    mean, var, used = np.array(mean, np.float64), np.array(var, np.float64), np.array(used, np.float64)
+    for c in np.unique(y):
+        e = x[y == c]
+        n = e.shape[0]
+        m = e.mean(0)
+        v = e.var(0)                                         # unbiased=False ...
+        if n > 1:
+            v = v * n / (n - 1)                              # ... rescaled to the unbiased estimate
+        if used[c] > 0:
+            mean[c] = decay * m + (1 - decay) * mean[c]
+            var[c] = decay * v + (1 - decay) * var[c]
+        else:
+            mean[c], var[c] = m, v
+            used[c] += 1
+    return mean, var, used
+
+
+def bce_dense(z, target, weight=None, pos_weight=None):
+    """binary_cross_entropy with already-expanded labels (cross_entropy_loss.py:100-106): elementwise loss * weight
+    and its z-gradient."""
+    loss, dz = bce_with_logits(z, np.asarray(target, np.float64), pos_weight)
+    if weight is not None:
+        w = np.asarray(weight, np.float64)
+        loss, dz = loss * w, dz * w
+    return loss, dz
+
+
 # ----------------------------------------------------------------------------------------
 # a9  accuracy
 # ----------------------------------------------------------------------------------------

@@ -115,7 +115,7 @@ def cpu_shims():
     """Run reference code that names CUDA on a CPU-only host (device remap only)."""
     import torch
 
-    real_tensor, real_zeros = torch.tensor, torch.zeros
+    real_tensor, real_zeros, real_ones = torch.tensor, torch.zeros, torch.ones
     real_cuda_ft = getattr(torch.cuda, "FloatTensor", None)
     real_t_cuda = torch.Tensor.cuda
 
@@ -124,7 +124,13 @@ def cpu_shims():
             k["device"] = "cpu"
         return real_tensor(*a, **k)
 
+    def ones(*a, **k):
+        if str(k.get("device", "")).startswith("cuda"):
+            k["device"] = "cpu"
+        return real_ones(*a, **k)
+
     torch.tensor = tensor
+    torch.ones = ones
     torch.cuda.FloatTensor = torch.FloatTensor
     torch.Tensor.cuda = lambda self, *a, **k: self
     try:
@@ -132,9 +138,36 @@ def cpu_shims():
     finally:
         torch.tensor = real_tensor
         torch.zeros = real_zeros
+        torch.ones = real_ones
         torch.Tensor.cuda = real_t_cuda
         if real_cuda_ft is not None:
             torch.cuda.FloatTensor = real_cuda_ft
+
+
+def load_functions(rel_path: str, names, class_name: str | None = None, extra_globals=None):
+    """The UNMODIFIED source of selected functions / methods of a reference file whose module cannot be imported
+    here (apex / mmcv / catalyst at import time): the file is parsed, the named FunctionDef nodes (module level, or
+    inside `class_name`) are compiled as they stand and returned in a dict.  Nothing is edited or copied."""
+    import ast
+
+    import numpy as np
+    import torch
+
+    path = os.path.join(REF, rel_path)
+    with open(path) as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    body = tree.body
+    if class_name is not None:
+        body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name).body
+    picked = [n for n in body if isinstance(n, ast.FunctionDef) and n.name in set(names)]
+    missing = set(names) - {n.name for n in picked}
+    if missing:
+        raise KeyError(f"{rel_path}: no function(s) {sorted(missing)}")
+    mod = ast.Module(body=picked, type_ignores=[])
+    ns = {"torch": torch, "np": np, "nn": torch.nn}
+    ns.update(extra_globals or {})
+    exec(compile(mod, path, "exec"), ns)
+    return {n: ns[n] for n in names}
 
 
 def csv_path(name: str) -> str:

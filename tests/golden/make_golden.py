@@ -304,6 +304,118 @@ def gen_mmdet_bce():
     np.savez_compressed(os.path.join(HERE, "mmdet_bce.npz"), **out)
 
 
+# ------------------------------------------------------------------ widened rows of round 2
+def gen_widen():
+    """cls NormedLinear / CosNorm_Classifier(lr_scale=True) (resnet_cifar.py:38-78), shot_acc (per_shot_acc.py:62-105),
+    mmdet binary_cross_entropy with already-expanded labels (cross_entropy_loss.py:100-106), FasaIIFLoss cums in sigmoid
+    mode and with a negative label (fasa_iif_loss.py:154-160), FasaBBoxHead.fa_update (fasa_bbox_head.py:118-148) --
+    all from the unmodified reference source."""
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    with ref_loader.cpu_shims():
+        rc = ref_loader.load_resnet_cifar()
+
+        def run(tag, mod, B, D, wscale):
+            mod = mod.double()
+            with torch.no_grad():
+                mod.weight.copy_(torch.randn(mod.weight.shape, generator=g, dtype=torch.float64) * wscale)
+            x = (torch.randn(B, D, generator=g, dtype=torch.float64) * 1.5).requires_grad_(True)
+            z = mod(x)
+            gz = torch.randn(z.shape, generator=g, dtype=torch.float64)
+            z.backward(gz)
+            out[f"{tag}_x"], out[f"{tag}_w"], out[f"{tag}_gz"], out[f"{tag}_z"] = npy(x), npy(mod.weight), npy(gz), npy(z)
+            out[f"{tag}_dx"], out[f"{tag}_dw"] = npy(x.grad), npy(mod.weight.grad)
+            return mod
+
+        run("cls_normed", rc.NormedLinear(64, 36), 24, 64, 0.3)
+        m = run("cosnorm_lr", rc.CosNorm_Classifier(64, 36, lr_scale=True), 24, 64, 0.1)
+        out["cosnorm_lr_scale"], out["cosnorm_lr_dscale"] = npy(m.scale), npy(m.scale.grad)
+
+    # ---- shot_acc
+    shot = ref_loader.load_functions("classification/per_shot_acc.py", ["shot_acc"])["shot_acc"]
+    C = 40
+    counts = [max(int(400 * (0.005) ** (c / (C - 1.0))), 1) for c in range(C)]
+    train = np.repeat(np.arange(C), counts)
+    labels = torch.randint(0, C, (600,), generator=g)
+    labels[labels == 7] = 8                                  # a class absent from the test labels
+    preds = torch.where(torch.rand(600, generator=g) < 0.6, labels, torch.randint(0, C, (600,), generator=g))
+    many, med, low, cacc = shot(preds, labels, train, acc_per_cls=True)
+    out.update(shot_counts=np.array(counts), shot_labels=npy(labels), shot_preds=npy(preds),
+               shot_out=np.array([many, med, low], np.float64), shot_class_acc=np.array(cacc, np.float64))
+    m2 = shot(preds, labels, train, many_shot_thr=1000, low_shot_thr=2)
+    out["shot_out_thr"] = np.array(m2, np.float64)           # empty many / low groups -> 0
+
+    # ---- dense-label BCE
+    B, C = 12, 37
+    z0 = torch.randn(B, C, generator=g) * 2
+    tgt = (torch.rand(B, C, generator=g) < 0.2).float()
+    soft = torch.rand(B, C, generator=g)
+    wel = torch.rand(B, C, generator=g)
+    wrow = torch.rand(B, 1, generator=g)
+    pw = (0.5 + torch.rand(C, generator=g))
+    out.update(bced_z=npy(z0), bced_t=npy(tgt), bced_soft=npy(soft), bced_wel=npy(wel), bced_wrow=npy(wrow), bced_pw=npy(pw))
+    bce = mm.cross_entropy_loss.binary_cross_entropy
+
+    def run_bce(tag, label, **kw):
+        z = z0.clone().requires_grad_(True)
+        loss = bce(z, label, **kw)
+        loss.sum().backward()
+        out[f"bced_loss_{tag}"], out[f"bced_dz_{tag}"] = npy(loss), npy(z.grad)
+
+    run_bce("mean", tgt)
+    run_bce("soft_sum", soft, reduction="sum")
+    run_bce("wel_avg", tgt, weight=wel, avg_factor=5.0)
+    run_bce("wrow_none", tgt, weight=wrow.expand(B, C), reduction="none")
+    run_bce("pw_mean", tgt, class_weight=pw)
+
+    # ---- FASA cums: sigmoid mode ([B,C] loss rows are summed) and a negative label (python indexing from the end)
+    with ref_loader.cpu_shims():
+        path = ref_loader.csv_path("idf_1204.csv")
+        Bc, Cc = 16, 1204
+        zc = torch.randn(Bc, Cc, generator=g)
+        yc = torch.randint(0, 1203, (Bc,), generator=g)
+        yc[3] = yc[5]
+        yc[9] = 1203
+        out.update(cum_z=npy(zc), cum_y=npy(yc))
+        crit = mm.fasa_iif_loss.FasaIIFLoss(path=path, variant="raw", num_classes=1203, use_cums=True, use_sigmoid=True)
+        r1 = crit(zc, yc)
+        out["cum_sig_losses"], out["cum_sig_labels"], out["cum_sig_ret"] = npy(crit.cum_losses), npy(crit.cum_labels), npy(r1)
+        crit = mm.fasa_iif_loss.FasaIIFLoss(path=path, variant="raw", num_classes=1203, use_cums=True)
+        yn = yc.clone()
+        yn[2] = -100                                         # ignored by the loss, binned at cum[-100] by the reference
+        r2 = crit(zc, yn)
+        out["cum_neg_y"] = npy(yn)
+        out["cum_neg_losses"], out["cum_neg_labels"], out["cum_neg_ret"] = npy(crit.cum_losses), npy(crit.cum_labels), npy(r2)
+
+    # ---- FASA feature statistics: the two methods of FasaBBoxHead, run as they stand on a bare object
+    fns = ref_loader.load_functions("instance_segmentation/mmdet/models/roi_heads/bbox_heads/fasa_bbox_head.py",
+                                    ["fa_update", "fa_update_push"], class_name="ConvFCFASABBoxHead")
+
+    class _Head:
+        pass
+
+    hd = _Head()
+    nb, D = 21, 48
+    hd.decay_ratio = 0.1
+    hd.feature_mean = torch.zeros(nb, D)
+    hd.feature_std = torch.zeros(nb, D)
+    hd.feature_used = torch.zeros(nb)
+    hd.fa_update_push = lambda e, l: fns["fa_update_push"](hd, e, l)
+    emb1 = torch.randn(64, D, generator=g)
+    lab1 = torch.randint(0, 12, (64,), generator=g)
+    lab1[0] = 19                                             # a class with a single row: variance 0
+    emb2 = torch.randn(40, D, generator=g) + 0.5
+    lab2 = torch.randint(4, 20, (40,), generator=g)
+    fns["fa_update"](hd, emb1, lab1)
+    out.update(fa_emb1=npy(emb1), fa_lab1=npy(lab1), fa_mean1=npy(hd.feature_mean), fa_std1=npy(hd.feature_std),
+               fa_used1=npy(hd.feature_used))
+    fns["fa_update"](hd, emb2, lab2)
+    out.update(fa_emb2=npy(emb2), fa_lab2=npy(lab2), fa_mean2=npy(hd.feature_mean), fa_std2=npy(hd.feature_std),
+               fa_used2=npy(hd.feature_used), fa_decay=np.float64(0.1))
+    np.savez_compressed(os.path.join(HERE, "widen.npz"), **out)
+    print("widen.npz", len(out), "arrays")
+
+
 # ------------------------------------------------------------------ CSV weight tables
 def gen_tables():
     out = {}
@@ -328,6 +440,7 @@ if __name__ == "__main__":
     gen_mmdet()
     gen_mmdet_bce()
     gen_tables()
+    gen_widen()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

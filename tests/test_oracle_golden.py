@@ -374,3 +374,52 @@ def test_oracle_properties_widened_rows():
     assert abs((f(x, wp) - f(x, wm)) / (2 * eps) - dw2[4, 1]) < 1e-5 * max(1.0, abs(dw2[4, 1]))
     zc, dxc, dwc = ho.cosnorm_classifier(x, w, gz)
     assert np.abs(zc).max() <= 16.0 + 1e-9          # |scale * cos| <= scale
+
+
+# ------------------------------------------------------------------ widened rows of round 2 (tests/golden/widen.npz)
+def test_widen_cls_normed_and_cosnorm_lr(golden):
+    g = golden("widen")
+    z, dx, dw = ho.cls_normed_linear(g["cls_normed_x"], g["cls_normed_w"], g["cls_normed_gz"])
+    close(z, g["cls_normed_z"]); close(dx, g["cls_normed_dx"]); close(dw, g["cls_normed_dw"])
+    z, dx, dw, ds = ho.cosnorm_classifier_lr(g["cosnorm_lr_x"], g["cosnorm_lr_w"], g["cosnorm_lr_gz"], g["cosnorm_lr_scale"])
+    close(z, g["cosnorm_lr_z"]); close(dx, g["cosnorm_lr_dx"]); close(dw, g["cosnorm_lr_dw"])
+    close([ds], g["cosnorm_lr_dscale"])
+
+
+def test_widen_shot_acc(golden):
+    g = golden("widen")
+    close(ho.shot_accuracy(g["shot_preds"], g["shot_labels"], g["shot_counts"]), g["shot_out"])
+    close(ho.shot_accuracy(g["shot_preds"], g["shot_labels"], g["shot_counts"], 1000, 2), g["shot_out_thr"])
+
+
+def test_widen_bce_dense(golden):
+    g = golden("widen")
+    z, B, C = g["bced_z"], *g["bced_z"].shape
+
+    def chk(tag, t, red, avgf=None, w=None, pw=None):
+        l, dz = ho.bce_dense(z, t, w, pw)
+        val, sc = ho.reduce_mmdet(l, red, avgf)
+        close(val, g[f"bced_loss_{tag}"]); close(dz * sc, g[f"bced_dz_{tag}"])
+
+    chk("mean", g["bced_t"], "mean")
+    chk("soft_sum", g["bced_soft"], "sum")
+    chk("wel_avg", g["bced_t"], "mean", 5.0, g["bced_wel"])
+    chk("wrow_none", g["bced_t"], "none", None, np.repeat(g["bced_wrow"], C, 1))
+    chk("pw_mean", g["bced_t"], "mean", None, None, g["bced_pw"])
+
+
+def test_widen_fasa_cums_and_stats(golden):
+    g = golden("widen")
+    l, _ = ho.sigmoid_bce_mmdet(g["cum_z"], g["cum_y"])                 # sigmoid mode: [B,C] loss, rows summed per class
+    cl, cn = ho.class_accumulate(g["cum_y"], l, 1204)
+    close(cl, g["cum_sig_losses"]); assert np.array_equal(cn, g["cum_sig_labels"]); close([l.mean()], [g["cum_sig_ret"]])
+    iif = ho.csv_column_to_weights(golden("weight_tables")["idf_1204_raw"])
+    li, _, _ = ho.softmax_ce(g["cum_z"], iif, g["cum_neg_y"])
+    cl, cn = ho.class_accumulate(g["cum_neg_y"], li, 1204)              # label -100 lands in bin 1204 - 100
+    close(cl, g["cum_neg_losses"]); assert np.array_equal(cn, g["cum_neg_labels"]) and cn[1104] == 1
+    close([li.mean()], [g["cum_neg_ret"]])
+    nb, D = g["fa_mean1"].shape
+    m, v, u = ho.class_feature_stats(g["fa_emb1"], g["fa_lab1"], np.zeros((nb, D)), np.zeros((nb, D)), np.zeros(nb), 0.1)
+    close(m, g["fa_mean1"]); close(v, g["fa_std1"]); assert np.array_equal(u, g["fa_used1"])
+    m, v, u = ho.class_feature_stats(g["fa_emb2"], g["fa_lab2"], m, v, u, float(g["fa_decay"]))
+    close(m, g["fa_mean2"]); close(v, g["fa_std2"]); assert np.array_equal(u, g["fa_used2"])

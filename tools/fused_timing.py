@@ -12,7 +12,8 @@ B, D, C = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256,2048,1000
 lib = _lib.load()
 bf = torch.bfloat16
 NAMES = ["start", "prologue", "griddep", "F_issued", "F_parked", "L_flags", "L_rows_done", "barrier", "B_issued",
-         "B_drained", "R_done", "end"]
+         "B_drained", "R_done", "end", "L_hook", "L_row_ret", "R_flags", "B_acc_last", "F_first_req", "F_full_first",
+         "F_full_last", "dX_full_first", "dX_full_last", "dW_full_first", "dW_full_last"]
 plan = (ctypes.c_int * 12)()
 rc = lib.iif_debug_fused_plan(B, D, C, 1, 148, plan)
 print("plan rc", rc, "grid/fS/fItems/dxS/dxItems/dwItems/dxFirst/tpr/ne/rowBlocks/partMB", list(plan)[:11])
@@ -28,17 +29,20 @@ for _ in range(3):
 torch.cuda.synchronize()
 
 def show(tag, flush):
-    buf = torch.zeros(4096 * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(4096 * 32, dtype=torch.int64, device=dev)
     if flush:
         big = torch.empty(512 << 20, dtype=torch.uint8, device=dev); big.zero_(); torch.cuda.synchronize()
     lib.iif_debug_timing_fused(buf.data_ptr())
     hs.launch()
     torch.cuda.synchronize()
     lib.iif_debug_timing_fused(None)
-    t = buf.cpu().numpy().reshape(-1, 16)
+    t = buf.cpu().numpy().reshape(-1, 32)
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
-    print(f"== {tag}: {len(t)} CTAs, kernel span {(t[:, :12].max() - t0) / 1e3:.2f} us")
+    print(f"== {tag}: {len(t)} CTAs, kernel span {(t[:, :32].max() - t0) / 1e3:.2f} us")
+    if tag.endswith("flushed"):
+        np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out",
+                             f"fused_stamps_{B}_{D}_{C}.npy"), t - t0)
     for i, n in enumerate(NAMES):
         col = t[:, i]
         col = col[col > 0]
