@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="256,2048,1000", help="B(per GPU),D,C")
     ap.add_argument("--variant", default="smooth")
+    ap.add_argument("--loss", default="softmax", choices=["softmax", "sigmoid"],
+                    help="softmax: IIF softmax-CE (the headline); sigmoid: mmdet sigmoid-BCE loss_cls (no IIF scale)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-loss", action="store_true", help="3 launches per step (loss rows in their own launch)")
@@ -62,6 +64,7 @@ def parse():
     ap.add_argument("--repeats", type=int, default=0, help="timed regions of --steps steps (median reported); 0 = auto")
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--no-e2e-alt", action="store_true", help="N=1: time only the staged host-batch mode")
+    ap.add_argument("--e2e-ring", action="store_true", help="N=1: also time the staged RING mode (one graph per S steps)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--sync-allreduce", action="store_true", help="N>1: all-reduce on the compute stream (no overlap)")
     ap.add_argument("--ar-ctas", type=int, default=0)
@@ -285,6 +288,163 @@ def torch_gpu_arm(B, D, C, dev, iif, prob, S, reps_target_s=0.25):
     return out
 
 
+def emit_line(args, L):
+    """Per-kernel timing, roofline, baselines and the JSON line (shared by the softmax and sigmoid arms)."""
+    import torch
+    import torch.distributed as dist
+    from iif_b200 import ops
+    (B, D, C, S, dev, sets, world, rank, cur, ms, region_ms, repeats, warm, value, loss_val, e2e, gpu_launches, clk,
+     launches_per_step, ring, use_graph, pipe_main, ar_kind, ar_check, iif, prob, per_set) = (L[k] for k in (
+         "B", "D", "C", "S", "dev", "sets", "world", "rank", "cur", "ms", "region_ms", "repeats", "warm", "value", "loss_val",
+         "e2e", "gpu_launches", "clk", "launches_per_step", "ring", "use_graph", "pipe_main", "ar_kind", "ar_check", "iif",
+         "prob", "per_set"))
+    # ---- per-kernel timing (rank 0): each kernel of the step alone, back to back over the rotating sets
+    pk = peaks()
+    kern = []
+    if rank == 0:
+        e = 2
+        algo = {  # algorithmic bytes / flops per launch (DESIGN.md section 4)
+            "linear_fwd_bf16": (e * (B * D + C * D) + 4 * B * C + 4 * C, 2.0 * B * D * C),
+            "softmax_ce_fwd_bwd": (4 * B * C + 2 * B * C + 8 * B + 8 * B + 4 * C, 0.0),
+            "sigmoid_bce_fwd_bwd": (4 * B * C + 2 * B * C + 8 * B + 8 * B, 0.0),
+            "linear_bwd_bf16": (2 * B * C + e * C * D + e * B * D + e * B * D + 4 * C * D + 4 * C, 4.0 * B * D * C),
+            # loss rows + dX + dW + db in one launch: Z in, dZ out (its re-read comes from L2), X, W in, dX, dW, db out
+            "loss_linear_bwd_bf16": (4 * B * C + 2 * B * C + 16 * B + 4 * C + e * C * D + e * B * D + e * B * D
+                                     + 4 * C * D + 4 * C, 4.0 * B * D * C),
+            # the whole step in one launch: X, W, labels, bias, iif in; Z (fp32, an API output), dZ (bf16, an API
+            # output), dX, dW, db out -- SURVEY.md 8(d) Q_ideal + the two outputs the drop-in API keeps
+            "head_step_fused_bf16": (e * B * D + e * C * D + 8 * B + 8 * C + 4 * B * C + 2 * B * C + e * B * D
+                                     + 4 * C * D + 4 * C + 4 * B, 6.0 * B * D * C),
+        }
+        names = [n for n, _ in sets[0].kernels()]
+        reps = max(1, 1200 // S)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for j, name in enumerate(names):
+            fns = [hs.kernels()[j][1] for hs in sets]
+            for f in fns:
+                f()
+            torch.cuda.synchronize(dev)
+            kg = torch.cuda.CUDAGraph()           # S launches of this one kernel, one per rotating set:
+            with torch.cuda.graph(kg):            # graph replay keeps the CPU launch path out of the timing
+                for f in fns:
+                    f()
+            kg.replay()
+            torch.cuda.synchronize(dev)
+            e0.record(cur)
+            for _ in range(reps):
+                kg.replay()
+            e1.record(cur)
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / (reps * S)
+            by, fl = algo[name]
+            t_hbm, t_tc = by / (pk["hbm"] * 1e9), fl / (pk["tf_burst"] * 1e12)
+            bound = "hbm" if t_hbm >= t_tc else "tensor"
+            ach = by / (us * 1e-6) / 1e9 if bound == "hbm" else fl / (us * 1e-6) / 1e12
+            peak = pk["hbm"] if bound == "hbm" else pk["tf_burst"]
+            kern.append({"kernel": name, "us": us, "bound": bound, "achieved": ach, "peak": peak,
+                         "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak, "algo_bytes": by,
+                         "flops": fl})
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        tot = sum(k["us"] for k in kern)
+        for k in kern:
+            k["share"] = k["us"] / tot
+        top = max(kern, key=lambda k: k["us"])
+        # BASELINE.md section 3: T_roof of the drop-in 4-kernel form (fwd, loss, dX, dW), sustained tensor peak
+        q4 = [(e * (B * D + C * D) + 4 * B * C + 8 * C, 2.0 * B * D * C), (8 * B * C + 16 * B + 4 * C, 0.0),
+              (4 * B * C + e * C * D + e * B * D, 2.0 * B * D * C), (4 * B * C + e * B * D + 4 * C * D + 4 * C, 2.0 * B * D * C)]
+        t_roof4 = sum(max(by / (pk["hbm"] * 1e9), fl / (pk["tf_sust"] * 1e12)) for by, fl in q4) * 1e6
+        roofline = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                    "frac": top["frac"], "traffic": None, "kernel": top["kernel"], "us_per_launch": top["us"],
+                    "peak_source": pk["src"] + (" burst" if top["bound"] == "tensor" else " copy"),
+                    "step_roofline_us": t_roof4,
+                    "step_roofline_def": "BASELINE.md s3: sum over {fwd, loss, dX, dW} of max(bytes/HBM, flops/sustained bf16)"}
+        roofline["step_frac"] = roofline["step_roofline_us"] / (ms * 1e3 / args.steps)
+        roofline["traffic"], roofline["traffic_source"] = ncu_traffic(top["kernel"], (B, D, C))
+        roofline["algo_bytes"] = top["algo_bytes"]
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline and args.loss == "softmax":
+            cpu = cpu_arm(B, D, C, args.cpu_seconds)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        tgb = None
+        if world == 1 and not args.no_torch_baseline and args.loss == "softmax":
+            tgb = torch_gpu_arm(B, D, C, dev, iif, prob, S)
+            tgb["ours_over_torch_graph_bf16"] = value / tgb["bf16"]["graph_samples_per_s"]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "repeats": repeats, "region_ms": {"median": ms, "min": min(region_ms), "max": max(region_ms)},
+                "config": {"workload": (WORKLOAD if (B, D, C) == (256, 2048, 1000) else f"IIF head {B}x{D}x{C}") +
+                                       (" [sigmoid-BCE loss_cls mode, no IIF scale]" if args.loss == "sigmoid" else ""),
+                           "loss": args.loss, "B_per_gpu": B, "D": D, "C": C, "global_batch": B * world, "variant": args.variant,
+                           "parallelism": f"dp{world} (row sharding, {ar_kind} all-reduce(mean) of dW+db "
+                                          f"{'on the compute stream' if args.sync_allreduce else 'overlapped on a side stream'})"
+                                          if world > 1 else "dp1",
+                           "launch": (f"cuda-graph replay (one graph = one step of each of the {S} sets, "
+                                      f"{launches_per_step} launch(es) per step)"
+                                      if ring is not None else
+                                      (f"cuda-graph replay (one graph = the {launches_per_step} launches of a step)"
+                                       if use_graph else ("eager, one C call per step (iif_pipeline_submit_device)"
+                                                          if pipe_main is not None else "eager"))),
+                           "l2": f"rotating {S} independent input+output sets, {S * per_set / 1e6:.0f} MB > 126 MB L2"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+                "kernels": kern, "cpu_baseline": cpu, "torch_gpu_baseline": tgb, "allreduce_check": ar_check,
+                "loss": loss_val}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
+
+# ------------------------------------------------------------------------------------------------
+# sigmoid mode: e2e through torch-level host batches + the JSON line (the C pipeline is the softmax step's API)
+# ------------------------------------------------------------------------------------------------
+def finish_sigmoid(args, L):
+    import torch
+    import torch.distributed as dist
+    B, D, C, S, dev, sets, world, rank = (L[k] for k in ("B", "D", "C", "S", "dev", "sets", "world", "rank"))
+    hx, hy, cur, graphs, fence = (L[k] for k in ("hx", "hy", "cur", "graphs", "fence"))
+    copy_s = torch.cuda.Stream(dev)
+    host_loss = torch.zeros(S).pin_memory()
+    evs = [torch.cuda.Event() for _ in range(S)]
+    cp_done = [torch.cuda.Event() for _ in range(S)]
+    n_e2e, lag = max(200, min(args.steps, 3000)), 4
+
+    def run(n):
+        last = 0.0
+        for i in range(n):
+            k = i % S
+            if i >= lag:
+                evs[(i - lag) % S].synchronize()
+                last = float(host_loss[(i - lag) % S])
+            with torch.cuda.stream(copy_s):                      # H2D of this step's batch (pinned -> device)
+                copy_s.wait_event(evs[k])                        # slot k's previous step is done with its inputs
+                sets[k]._x.copy_(hx[i % 4], non_blocking=True)
+                sets[k]._y.copy_(hy[i % 4], non_blocking=True)
+                cp_done[k].record(copy_s)
+            cur.wait_event(cp_done[k])
+            (graphs[k].replay() if graphs[k] is not None else sets[k].launch())
+            host_loss[k:k + 1].copy_(sets[k].loss.reshape(1), non_blocking=True)
+            evs[k].record(cur)
+        torch.cuda.synchronize(dev)
+        return last
+
+    for k in range(S):
+        evs[k].record(cur)
+    run(2 * S)
+    t0 = time.perf_counter()
+    last = run(n_e2e)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    L["e2e"] = {"value": world * B * n_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * D * 2 + B * 8,
+                "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e, "loss_read_lag_steps": lag,
+                "api": "iif_b200.ops.SigmoidHeadStep fed from pinned host batches (torch copy stream + CUDA-graph replay)",
+                "last_loss": last, "modes": None}
+    return emit_line(args, L)
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -345,10 +505,15 @@ def main():
         w = ((torch.rand(C, D, generator=g) * 2 - 1) / D ** 0.5).to(dev).to(torch.bfloat16)
         y = torch.multinomial(prob, B, replacement=True, generator=g).to(dev)
         bias = torch.full((C,), 0.01, device=dev)
-        hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws,
-                          fused_loss=not args.no_fused_loss, persistent=not args.no_persistent,
-                          grad_flat=None if peer is None else peer.buffer(s))
-        hs.bind(x, w, bias, iif, y)
+        if args.loss == "sigmoid":
+            hs = ops.SigmoidHeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws,
+                                     grad_flat=None if peer is None else peer.buffer(s))
+            hs.bind(x, w, bias, y)
+        else:
+            hs = ops.HeadStep(B, D, C, dev, need_dx=True, dx_bf16=True, need_db=True, ws=shared_ws,
+                              fused_loss=not args.no_fused_loss, persistent=not args.no_persistent,
+                              grad_flat=None if peer is None else peer.buffer(s))
+            hs.bind(x, w, bias, iif, y)
         sets.append(hs)
     launches_per_step = sets[0].launches_per_step
     cur = torch.cuda.current_stream(dev)
@@ -433,7 +598,7 @@ def main():
     # the host is not the bottleneck of a ~15 us step; events are recorded on the pipeline's own streams.
     pipe_main = None
     p_compute = None
-    if world > 1 and peer is not None and not args.sync_allreduce and not args.py_loop:
+    if world > 1 and peer is not None and not args.sync_allreduce and not args.py_loop and args.loss == "softmax":
         pipe_main = ops.HeadPipeline(sets)
         pipe_main.set_allreduce(peer)
         _, p_compute, _, _ = pipe_main.streams()
@@ -507,6 +672,8 @@ def main():
     hy = [torch.multinomial(prob, B, replacement=True, generator=g).pin_memory() for _ in range(4)]
     if pipe_main is not None:
         pipe_main.close()
+    if args.loss == "sigmoid":
+        return finish_sigmoid(args, locals())
     pipe = ops.HeadPipeline(sets)
     if world > 1 and peer is not None:
         pipe.set_allreduce(peer)
@@ -521,8 +688,23 @@ def main():
             sx.copy_(hx[k % 4])
             sy.copy_(hy[k % 4])
 
+    e2e_ring = False               # staged ring: ONE graph launch per S steps (iif_pipeline_submit_staged_ring)
+
     def e2e_run(n):
-        nonlocal staged
+        if e2e_ring:
+            # n is a multiple of S here; the losses of ring r are read (device -> host, per slot) after ring r + 1 has
+            # been submitted -- asynchronous logging with a lag of one ring
+            for r in range(n // S):
+                pipe.submit_staged_ring()
+                if r >= 1:
+                    pass                                        # (ring r - 1 finished before ring r started: stream order)
+                if r + 1 == n // S:
+                    for k in range(S):
+                        e2e_loss[0] = pipe.wait(k)
+                else:
+                    e2e_loss[0] = pipe.wait(S - 1 - min(lag, S - 1))   # a loss of the ring in flight, lag steps behind its tail
+            pipe.sync()
+            return
         for i in range(n):
             k = i % S
             if i >= lag:
@@ -542,9 +724,10 @@ def main():
             comm.synchronize()
 
     n_e2e = max(200, min(args.steps, 3000))
+    n_e2e = (n_e2e + S - 1) // S * S               # whole rings
 
     def e2e_time():
-        e2e_run(max(32, S + 4))
+        e2e_run(max(32, 2 * S))
         fence()
         t0 = time.perf_counter()
         e2e_run(n_e2e)
@@ -552,125 +735,44 @@ def main():
         fence()
         return ms_
 
-    # N = 1: both host-batch modes of the public API are timed -- the staged mode costs one driver call per step
-    # (robust on a slow / shared host) but pays the GPU-side gap between graph launches; the event-driven mode
-    # costs ~11 driver calls per step and wins on a fast host.  The faster one is reported, the other kept.
-    e2e_ms = min(e2e_time() for _ in range(3))
+    # N = 1: the host-batch modes of the public API are timed -- the staged per-step graph (one driver call per step: the
+    # H2D of the next slot's batch rides next to this slot's kernel inside the graph, the loss is stored by the kernel
+    # into mapped pinned memory), the event-driven submit (~6 driver calls per step) and, with --e2e-ring, the staged
+    # RING (one graph launch per S steps).  The fastest is reported, the others kept in `modes`.
     e2e_alt = None
-    if staged and not args.no_e2e_alt:
-        staged_ms = e2e_ms
-        staged = False
+    if staged:
+        modes = {}
+        if args.e2e_ring:
+            e2e_ring = True
+            modes["staged_ring_ms_per_step"] = min(e2e_time() for _ in range(3)) / n_e2e
+            e2e_ring = False
+        modes["staged_ms_per_step"] = min(e2e_time() for _ in range(3)) / n_e2e
+        if not args.no_e2e_alt:
+            staged = False
+            modes["event_driven_ms_per_step"] = min(e2e_time() for _ in range(3)) / n_e2e
+        best = min(modes, key=modes.get)
+        e2e_ms = modes[best] * n_e2e
+        e2e_alt = modes
+        e2e_api = {"staged_ring_ms_per_step": "iif_b200.ops.HeadPipeline staged ring (iif_pipeline_submit_staged_ring / "
+                   "iif_pipeline_wait): pinned host staging -> H2D of every slot's batch inside ONE CUDA graph per "
+                   f"{S} steps, next to the previous slot's kernel; loss stored by the kernel into mapped pinned memory",
+                   "staged_ms_per_step": "iif_b200.ops.HeadPipeline staged mode (iif_pipeline_submit_staged / iif_pipeline_wait): "
+                   "pinned host staging -> H2D of the next batch inside the step's CUDA graph; loss stored by the kernel "
+                   "into mapped pinned memory",
+                   "event_driven_ms_per_step": "iif_b200.ops.HeadPipeline (iif_pipeline_submit / iif_pipeline_wait)"}[best]
+    else:
         e2e_ms = min(e2e_time() for _ in range(3))
-        e2e_alt = {"staged_ms_per_step": staged_ms / n_e2e, "event_driven_ms_per_step": e2e_ms / n_e2e}
-        if staged_ms < e2e_ms:
-            e2e_ms, staged = staged_ms, True
+        e2e_api = "iif_b200.ops.HeadPipeline (iif_pipeline_submit / iif_pipeline_wait)"
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e = {"value": world * B * n_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * D * 2 + B * 8,
            "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e, "loss_read_lag_steps": lag,
-           "api": ("iif_b200.ops.HeadPipeline staged mode (iif_pipeline_submit_staged / iif_pipeline_wait): pinned host "
-                   "staging -> H2D of the next batch inside the step's CUDA graph; loss stored by the kernel into "
-                   "mapped pinned memory") if staged else
-                  "iif_b200.ops.HeadPipeline (iif_pipeline_submit / iif_pipeline_wait)", "last_loss": e2e_loss[0], "modes": e2e_alt}
+           "api": e2e_api, "last_loss": e2e_loss[0], "modes": e2e_alt}
     pipe.close()
 
-    # ---- per-kernel timing (rank 0): each kernel of the step alone, back to back over the rotating sets
-    pk = peaks()
-    kern = []
-    if rank == 0:
-        e = 2
-        algo = {  # algorithmic bytes / flops per launch
-            "linear_fwd_bf16": (e * (B * D + C * D) + 4 * B * C + 4 * C, 2.0 * B * D * C),
-            "softmax_ce_fwd_bwd": (4 * B * C + 2 * B * C + 8 * B + 8 * B + 4 * C, 0.0),
-            "linear_bwd_bf16": (2 * B * C + e * C * D + e * B * D + e * B * D + 4 * C * D + 4 * C, 4.0 * B * D * C),
-            # loss rows + dX + dW + db in one launch: Z in, dZ out (its re-read comes from L2), X, W in, dX, dW, db out
-            "loss_linear_bwd_bf16": (4 * B * C + 2 * B * C + 16 * B + 4 * C + e * C * D + e * B * D + e * B * D
-                                     + 4 * C * D + 4 * C, 4.0 * B * D * C),
-            # the whole step in one launch: X, W, labels, bias, iif in; Z (fp32, an API output), dZ (bf16, an API
-            # output), dX, dW, db out -- SURVEY.md 8(d) Q_ideal + the two outputs the drop-in API keeps
-            "head_step_fused_bf16": (e * B * D + e * C * D + 8 * B + 8 * C + 4 * B * C + 2 * B * C + e * B * D
-                                     + 4 * C * D + 4 * C + 4 * B, 6.0 * B * D * C),
-        }
-        names = [n for n, _ in sets[0].kernels()]
-        reps = max(1, 1200 // S)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for j, name in enumerate(names):
-            fns = [hs.kernels()[j][1] for hs in sets]
-            for f in fns:
-                f()
-            torch.cuda.synchronize(dev)
-            kg = torch.cuda.CUDAGraph()           # S launches of this one kernel, one per rotating set:
-            with torch.cuda.graph(kg):            # graph replay keeps the CPU launch path out of the timing
-                for f in fns:
-                    f()
-            kg.replay()
-            torch.cuda.synchronize(dev)
-            e0.record(cur)
-            for _ in range(reps):
-                kg.replay()
-            e1.record(cur)
-            torch.cuda.synchronize(dev)
-            us = e0.elapsed_time(e1) * 1e3 / (reps * S)
-            by, fl = algo[name]
-            t_hbm, t_tc = by / (pk["hbm"] * 1e9), fl / (pk["tf_burst"] * 1e12)
-            bound = "hbm" if t_hbm >= t_tc else "tensor"
-            ach = by / (us * 1e-6) / 1e9 if bound == "hbm" else fl / (us * 1e-6) / 1e12
-            peak = pk["hbm"] if bound == "hbm" else pk["tf_burst"]
-            kern.append({"kernel": name, "us": us, "bound": bound, "achieved": ach, "peak": peak,
-                         "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak, "algo_bytes": by,
-                         "flops": fl})
-    if world > 1:
-        dist.barrier()
-
-    if rank == 0:
-        tot = sum(k["us"] for k in kern)
-        for k in kern:
-            k["share"] = k["us"] / tot
-        top = max(kern, key=lambda k: k["us"])
-        # T_roof of the drop-in 4-kernel form (fwd, loss, dX, dW), sustained tensor peak
-        q4 = [(e * (B * D + C * D) + 4 * B * C + 8 * C, 2.0 * B * D * C), (8 * B * C + 16 * B + 4 * C, 0.0),
-              (4 * B * C + e * C * D + e * B * D, 2.0 * B * D * C), (4 * B * C + e * B * D + 4 * C * D + 4 * C, 2.0 * B * D * C)]
-        t_roof4 = sum(max(by / (pk["hbm"] * 1e9), fl / (pk["tf_sust"] * 1e12)) for by, fl in q4) * 1e6
-        roofline = {"bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
-                    "frac": top["frac"], "traffic": None, "kernel": top["kernel"], "us_per_launch": top["us"],
-                    "peak_source": pk["src"] + (" burst" if top["bound"] == "tensor" else " copy"),
-                    "step_roofline_us": t_roof4,
-                    "step_roofline_def": "BASELINE.md s3: sum over {fwd, loss, dX, dW} of max(bytes/HBM, flops/sustained bf16)"}
-        roofline["step_frac"] = roofline["step_roofline_us"] / (ms * 1e3 / args.steps)
-        roofline["traffic"], roofline["traffic_source"] = ncu_traffic(top["kernel"], (B, D, C))
-        roofline["algo_bytes"] = top["algo_bytes"]
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_arm(B, D, C, args.cpu_seconds)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        tgb = None
-        if world == 1 and not args.no_torch_baseline:
-            tgb = torch_gpu_arm(B, D, C, dev, iif, prob, S)
-            tgb["ours_over_torch_graph_bf16"] = value / tgb["bf16"]["graph_samples_per_s"]
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "repeats": repeats, "region_ms": {"median": ms, "min": min(region_ms), "max": max(region_ms)},
-                "config": {"workload": WORKLOAD if (B, D, C) == (256, 2048, 1000) else f"IIF head {B}x{D}x{C}",
-                           "B_per_gpu": B, "D": D, "C": C, "global_batch": B * world, "variant": args.variant,
-                           "parallelism": f"dp{world} (row sharding, {ar_kind} all-reduce(mean) of dW+db "
-                                          f"{'on the compute stream' if args.sync_allreduce else 'overlapped on a side stream'})"
-                                          if world > 1 else "dp1",
-                           "launch": (f"cuda-graph replay (one graph = one step of each of the {S} sets, "
-                                      f"{launches_per_step} launch(es) per step)"
-                                      if ring is not None else
-                                      (f"cuda-graph replay (one graph = the {launches_per_step} launches of a step)"
-                                       if use_graph else ("eager, one C call per step (iif_pipeline_submit_device)"
-                                                          if pipe_main is not None else "eager"))),
-                           "l2": f"rotating {S} independent input+output sets, {S * per_set / 1e6:.0f} MB > 126 MB L2"},
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
-                "kernels": kern, "cpu_baseline": cpu, "torch_gpu_baseline": tgb, "allreduce_check": ar_check,
-                "loss": loss_val}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return emit_line(args, locals())
 
 
 if __name__ == "__main__":

@@ -62,9 +62,11 @@ SIGNATURES = {
     "iif_row_dot": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _p, _p]),
     "iif_rows_axpby": (_i32, [_p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _p, _i64, _p]),
     "iif_scale_rows": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _p, _i32, _i64, _p]),
+    "iif_scale_inplace": (_i32, [_p, _i32, _i64, _p, _p]),
     "iif_colsum": (_i32, [_p, _i32, _i64, _p, _i64, _i64, _p, _p]),
     "iif_linear_fwd_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p, _sz, _p]),
     "iif_linear_fwd_f32": (_i32, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p]),
+    "iif_split3_bf16": (_i32, [_p, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p]),
     "iif_linear_bwd_dx_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _i32, _i64, _i64, _i64, _i64, _p, _sz, _p]),
     "iif_linear_bwd_dx_f32": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "iif_linear_bwd_dw_bf16": (_i32, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _p, _sz, _p]),
@@ -88,6 +90,7 @@ SIGNATURES = {
     "iif_pipeline_enable_staged": (_i32, [_p]),
     "iif_pipeline_staging": (_i32, [_p, _i32, C.POINTER(_p), C.POINTER(_p), C.POINTER(_p)]),
     "iif_pipeline_submit_staged": (_i32, [_p, _i32]),
+    "iif_pipeline_submit_staged_ring": (_i32, [_p]),
     "iif_pipeline_wait": (_i32, [_p, _i32]),
     "iif_pipeline_stream_wait_step": (_i32, [_p, _i32, _p]),
     "iif_pipeline_hold_slot": (_i32, [_p, _i32, _p]),

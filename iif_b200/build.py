@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libiif_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp")
-SOURCES = ["capi.cu", "loss.cu", "hist.cu", "gemm_f32.cu", "gemm_tc.cu", "head_fused.cu", "pipeline.cu", "allreduce.cu", "norm.cu", "widen.cu"]
+SOURCES = ["capi.cu", "loss.cu", "hist.cu", "gemm_f32.cu", "gemm_tc.cu", "head_fused.cu", "pipeline.cu", "allreduce.cu", "norm.cu", "widen.cu", "split3.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr"]

@@ -23,7 +23,7 @@
 namespace iif {
 
 constexpr int AR_MAX_WORLD = 16;
-constexpr int AR_MAX_CTAS = 64;
+constexpr int AR_MAX_CTAS = 192;          // up to one (or a little more than one) CTA per SM
 constexpr int AR_THREADS = 256;          // larger CTAs need an SM to themselves and have dead-locked against the GEMM grids
 constexpr int AR_LANES = 4;             // independent flag sets: up to 4 all-reduces of one rank may be in flight
 constexpr size_t AR_LANE_WORDS = (size_t)AR_MAX_CTAS * AR_MAX_WORLD + AR_MAX_CTAS;

@@ -36,6 +36,12 @@
 #ifndef HF_MIN_BLOCKS
 #define HF_MIN_BLOCKS 1
 #endif
+// Register cap of the step kernel: 168 x 256 threads = 42 K of the SM's 64 K registers, so that a 256-thread CTA of the
+// data-parallel all-reduce kernel (<= 80 registers per thread) can be co-resident with a step CTA -- without that room
+// the all-reduce of step k could only run in the gaps between step launches instead of under them.
+#ifndef HF_MAX_REGS
+#define HF_MAX_REGS 168
+#endif
 
 namespace iif {
 namespace hf {
@@ -164,20 +170,21 @@ __device__ __forceinline__ void load_logits(const Args& g, int64_t row, bool act
                                             float4 (&z4)[NE / 4]) {
   constexpr int NQ = NE / 4;
   constexpr int QG = NQ < 2 ? NQ : 2;                // float4 columns per batch: QG x MAX_SPLITS loads in flight
+  constexpr int SMAX = MAX_SPLITS;
   const int t = threadIdx.x % TPR, C = g.loss.C, S = g.f.splits;
   const int mi = (int)(row >> 7), r = (int)(row & 127);
   float* zrow = g.loss.z ? const_cast<float*>(g.loss.z) + row * g.loss.ldz : nullptr;
   const bool zvec = (g.loss.ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(g.loss.z) & 15u) == 0;
 #pragma unroll
   for (int q0 = 0; q0 < NQ; q0 += QG) {
-    float4 tt[QG][MAX_SPLITS];
+    float4 tt[QG][SMAX];
 #pragma unroll
     for (int u = 0; u < QG; ++u) {
       const int col = ((q0 + u) * TPR + t) * 4;
       if (active && col < C) {
         const float4* p = g.part + ((int64_t)(mi * g.f.tiles_n + (col >> 7)) * S * TM + r) * (TN / 4) + ((col & 127) >> 2);
 #pragma unroll
-        for (int s = 0; s < MAX_SPLITS; ++s)
+        for (int s = 0; s < SMAX; ++s)
           if (s < S) tt[u][s] = __ldcg(p + (int64_t)s * TILE_F4);
       }
     }
@@ -190,7 +197,7 @@ __device__ __forceinline__ void load_logits(const Args& g, int64_t row, bool act
       }
       float4 acc = tt[u][0];
 #pragma unroll
-      for (int s = 1; s < MAX_SPLITS; ++s)           // fixed split order: deterministic
+      for (int s = 1; s < SMAX; ++s)                 // fixed split order: deterministic
         if (s < S) { acc.x += tt[u][s].x; acc.y += tt[u][s].y; acc.z += tt[u][s].z; acc.w += tt[u][s].w; }
       acc.x += b4[q].x; acc.y += b4[q].y; acc.z += b4[q].z; acc.w += b4[q].w;
       const bool full = col + 4 <= C;
@@ -274,7 +281,7 @@ __device__ __forceinline__ void reduce_dx(const Args& g, const int* ctrs) {
 
 // TPR threads per loss row, NE logits per thread (C <= TPR * NE), 256 / TPR rows per CTA pass.
 template <int TPR, int NE>
-__global__ void __launch_bounds__(256, HF_MIN_BLOCKS)
+__global__ void __maxnreg__(HF_MAX_REGS)
 head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmP,
                   const __grid_constant__ CUtensorMap tmDW, const __grid_constant__ Args g) {
@@ -324,11 +331,15 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   ptx::griddep_launch_dependents();
   ptx::griddep_wait();                               // the previous launch of the stream (same workspace) is complete
   if (threadIdx.x == 0) stamp(g, 2);
-  const int parity = __ldcg(g.ctr) & 1;              // (stable until the last CTA passes the grid barrier)
-  int* const ctrs = g.ctr + CTR_SET0 + parity * CTR_SET_STRIDE;
+  // The single producer thread runs scalar code at a few cycles per instruction: only the first forward item is
+  // decoded in front of the first TMA requests, everything else behind them.
+  const int nF = my_items(g.f.items);
+  const Item itF0 = decode_f(g, nF > 0 ? snake(0, g.f.items) : 0);
 
   constexpr int NQ = NE / 4;
   constexpr int RPB = 256 / TPR;
+  int parity = 0;
+  int* ctrs = nullptr;                               // counter set of this launch: set after the first operand requests
 
   // ---- pipeline state.  Producer (thread 0): ring position of load #0 of the NEXT item to be (fully) issued, and
   // how many A / B parts of that item are already in flight.  MMA issuer (thread 32): its own ring position.
@@ -473,35 +484,58 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     ptx::tc_fence_before();
     __syncthreads();                                 // accumulator + staging reusable; every warp's park is complete
     ptx::tc_fence_after();
-    if (it.kind != 2 && threadIdx.x == 0) ptx::red_release_add(ctrs + it.ctr_idx, 1);
+    if (it.kind != 2 && threadIdx.x == 0)   // (counter set from the parity word: first use, long after its load was issued)
+      ptx::red_release_add(g.ctr + CTR_SET0 + (parity & 1) * CTR_SET_STRIDE + it.ctr_idx, 1);
   };
 
   // ============================ phase F ============================
-  const int nF = my_items(g.f.items);
   if (threadIdx.x == 0 && nF > 0) {
-    produce(decode_f(g, snake(0, g.f.items)), STAGES, true, true);
+    // first fill of a ring nobody has touched: no empty-slot waits
+    const int n0 = itF0.cnt < STAGES ? itF0.cnt : STAGES;
+    for (int i = 0; i < n0; ++i) {
+      const int kb = itF0.split + i * itF0.nsplit;
+      load_b(itF0, i, kb);
+      load_a(itF0, i, kb);
+    }
+    pre_a = pre_b = n0;
     stamp(g, 16);
   }
+  // Counter set of this launch (stable until the last CTA passes the grid barrier).  Loaded AFTER the first operand
+  // requests: an in-order warp stalls at the first USE of a load, and that use must not sit in front of the TMA issue.
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(parity) : "l"(g.ctr));
+  const int nB = g.dx.items + g.dw.items;
+  const int my_b = my_items(nB);
+  const Item itB0 = decode_b(g, my_b > 0 ? snake(0, nB) : 0);
+
   // The label-dependent scalars, IIF weights and bias of this CTA's FIRST loss-row block do not depend on the
   // forward product: their (HBM-cold) loads are issued now -- after the operand requests of the first forward
   // item, which must not queue behind the label -> class-weight dependency -- and land under phase F.
+  constexpr bool PRE_BIAS = NE <= 8;                 // (wide rows: NQ float4 of bias held across phase F would spill)
   RowHead<TPR, NE> head0;
-  float4 bias0[NQ];
-  if ((int)blockIdx.x < g.row_blocks) {
-    row_head<TPR, NE, 0>(g.loss, blockIdx.x, head0);
-    load_bias<TPR, NE>(g, head0.active, bias0);
-  }
+  float4 bias0[PRE_BIAS ? NQ : 1];
+  auto prefetch_head = [&]() {
+    if ((int)blockIdx.x < g.row_blocks) {
+      row_head<TPR, NE, 0>(g.loss, blockIdx.x, head0);
+      if constexpr (PRE_BIAS) load_bias<TPR, NE>(g, head0.active, bias0);
+    }
+  };
+  // The two ROLE threads must not stall on these loads (an in-order thread waits at the first use of a loaded value,
+  // and the label -> class-weight chain is two HBM round trips): they prefetch after their role work of the first
+  // forward item is issued; everybody else -- with nothing to do until the accumulator is complete -- prefetches now.
+  const bool role_thread = threadIdx.x == 0 || threadIdx.x == 32;
+  if (!role_thread || nF == 0) prefetch_head();
   {
     const int n = nF;
     for (int k = 0; k < n; ++k) {
-      const Item it = decode_f(g, snake(k, g.f.items));
+      const Item it = k == 0 ? itF0 : decode_f(g, snake(k, g.f.items));
       if (threadIdx.x == 0) {
         produce(it, it.cnt, true, true);
         producer_next_item(it);
         if (k + 1 < n) produce(decode_f(g, snake(k + 1, g.f.items)), STAGES, true, true);
-        if (k == 0) stamp(g, 3);
+        if (k == 0) { stamp(g, 3); prefetch_head(); }
       } else if (threadIdx.x == 32) {
         mma_item(it);
+        if (k == 0) prefetch_head();
       }
       __syncwarp();
       drain_item(it);
@@ -511,13 +545,11 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   // first backward item of this CTA: its B operand (X / W tiles) does not depend on the loss -- requested from
   // inside the first loss row (or right here when the CTA has no rows)
-  const int nB = g.dx.items + g.dw.items;
-  const int my_b = my_items(nB);
   bool b_issued = false;
   auto issue_b = [&]() {
     if (threadIdx.x == 0 && !b_issued) {
       stamp(g, 12);                                  // first loss row: loads returned, first reduction done
-      if (my_b > 0) produce(decode_b(g, snake(0, nB)), STAGES, false, true);
+      if (my_b > 0) produce(itB0, STAGES, false, true);
     }
     b_issued = true;
   };
@@ -526,6 +558,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   double loss_part = 0.0;
   int loss_c1 = 0, loss_c5 = 0;
   {
+    parity &= 1;
+    ctrs = g.ctr + CTR_SET0 + parity * CTR_SET_STRIDE;
     __shared__ RowSmem<256> row_sm;
     __shared__ float s_row_loss[256 / TPR];
     __shared__ int s_row_rank[256 / TPR];
@@ -535,8 +569,12 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       float4 b4[NQ], z4[NQ];
       if (rb == (int)blockIdx.x) {
         hd = head0;
+        if constexpr (PRE_BIAS) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) b4[q] = bias0[q];
+          for (int q = 0; q < NQ; ++q) b4[q] = bias0[q];
+        } else {
+          load_bias<TPR, NE>(g, hd.active, b4);
+        }
       } else {
         row_head<TPR, NE, 0>(g.loss, rb, hd);           // (in flight while thread 0 polls the m-tile's counter)
         load_bias<TPR, NE>(g, hd.active, b4);
@@ -588,7 +626,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       ptx::spin_until_ge(ctrs + CTR_ROWS, (int)gridDim.x);
       asm volatile("fence.proxy.async;" ::: "memory");
       stamp(g, 7);
-      if (my_b > 0) produce(decode_b(g, snake(0, nB)), STAGES, true, true);
+      if (my_b > 0) produce(itB0, STAGES, true, true);
     }
     if (warp == 3) {
       // Duties of the LAST CTA to arrive (it knows every CTA's partials are published), done by an otherwise idle warp
@@ -618,7 +656,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
     for (int k = 0; k < my_b; ++k) {
-      const Item it = decode_b(g, snake(k, nB));
+      const Item it = k == 0 ? itB0 : decode_b(g, snake(k, nB));
       if (threadIdx.x == 0) {
         produce(it, it.cnt, true, true);
         producer_next_item(it);
@@ -713,6 +751,10 @@ static bool make_plan(int64_t B, int64_t D, int64_t C, bool need_dx, int sms, Pl
     pl.dx.splits = best_s; pl.dx.items = tiles * best_s;
     pl.b_dx_first = (pl.dx.kb_total + best_s - 1) / best_s >= pl.dw.kb_total;
   }
+  // loss-row geometry: a pass of the row loop is latency (one L2 round trip, two block reductions), so batches with
+  // many rows per CTA take MORE ROWS PER PASS (fewer threads per row, more logits per thread)
+  // (measured: more rows per pass -- 64 threads x 32 logits -- is SLOWER for the LVIS shapes: the wide per-thread
+  // state spills under the register cap; the three narrow geometries stay)
   if (C <= 1024) { pl.tpr = 128; pl.ne = 8; }
   else if (C <= 2048) { pl.tpr = 256; pl.ne = 8; }
   else { pl.tpr = 256; pl.ne = 16; }

@@ -257,6 +257,25 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// data *= *g in place over a flat buffer; returns at once when *g == 1 (the upstream gradient of a loss that is
+// the autograd root): the one-launch head step forms dX / dW / db in the FORWARD call with g = 1 and the autograd
+// backward only has to apply the actual upstream scalar -- almost always exactly 1.
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256) scale_inplace_kernel(void* __restrict__ data, int64_t n, const float* __restrict__ g) {
+  const float gv = __ldg(g);
+  if (gv == 1.f) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if constexpr (BF16) {
+      __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(data) + i;
+      *p = __float2bfloat16_rn(__bfloat162float(*p) * gv);
+    } else {
+      reinterpret_cast<float*>(data)[i] *= gv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // db[c] = alpha * sum_i dz[i,c]: 32 columns per CTA, 8 row lanes, fixed-order tree
 // ------------------------------------------------------------------------------------------------
 template <bool BF16>
@@ -383,6 +402,16 @@ extern "C" int iif_scale_rows(const float* in, int64_t ldi, const float* g, int6
   else if (vec) scale_rows_kernel<true, false><<<grid, 256, 0, st>>>(in, ldi, g, g_stride, rows, (int)cols, out, ldo);
   else if (bf) scale_rows_kernel<false, true><<<grid, 256, 0, st>>>(in, ldi, g, g_stride, rows, (int)cols, out, ldo);
   else scale_rows_kernel<false, false><<<grid, 256, 0, st>>>(in, ldi, g, g_stride, rows, (int)cols, out, ldo);
+  return launch_status();
+}
+
+extern "C" int iif_scale_inplace(void* data, int dtype, int64_t n, const float* g_dev, void* stream) {
+  if (n < 0 || !g_dev || (dtype != IIF_DTYPE_F32 && dtype != IIF_DTYPE_BF16)) return IIF_EINVAL;
+  if (n == 0) return IIF_OK;
+  if (!data) return IIF_EINVAL;
+  const unsigned grid = (unsigned)((n + 255) / 256 < 8 * kNumSMs ? (n + 255) / 256 : 8 * kNumSMs);
+  if (dtype == IIF_DTYPE_BF16) scale_inplace_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(data, n, g_dev);
+  else scale_inplace_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(data, n, g_dev);
   return launch_status();
 }
 

@@ -18,6 +18,9 @@ struct iif_pipeline {
     cudaEvent_t h2d_done, step_done, loss_done, release;
     bool used, held;
     bool device_only;                  // latest step came from submit_device: no loss was copied to the host
+    bool waited;                       // the host has synchronised on the latest step (iif_pipeline_wait): buffers are free
+    // host-batch submits: the loss goes straight into the caller's pinned host word when it is device-addressable
+    float* direct_host; float* direct_dev; iif_head_args a_direct; bool direct_last;
     int64_t ar_offset;
     // staged mode (iif_pipeline_enable_staged): library-owned pinned host staging + one CUDA graph per slot
     void* host_x; int64_t* host_y; float* host_loss;   // pinned; host_loss is mapped (the kernel stores into it)
@@ -29,6 +32,7 @@ struct iif_pipeline {
   cudaStream_t s_h2d, s_compute, s_d2h, s_comm[4];
   int ar_lanes, ar_next;
   bool staged; int primed;               // slot whose inputs are already on the device (prefetched), or -1
+  cudaGraphExec_t ring_exec; int ring_launches;   // staged mode: ONE graph holding a step of every slot (see enable_staged)
   Slot* slots;
   // optional data-parallel exchange after every step (iif_pipeline_set_allreduce)
   bool ar_on;
@@ -87,9 +91,9 @@ extern "C" int iif_pipeline_set_allreduce(iif_pipeline* p, void* const* peer_buf
 }
 
 // the step on the compute stream, then (data-parallel runs) the all-reduce of its gradients on the comm stream
-static int run_step(iif_pipeline* p, iif_pipeline::Slot& s) {
+static int run_step(iif_pipeline* p, iif_pipeline::Slot& s, const iif_head_args* args = nullptr) {
   if (s.held) { IIF_CU(cudaStreamWaitEvent(p->s_compute, s.release, 0)); s.held = false; }  // gradients still in flight
-  if (int rc = iif_head_fwd_bwd_bf16(&s.a, p->s_compute)) return rc;
+  if (int rc = iif_head_fwd_bwd_bf16(args ? args : &s.a, p->s_compute)) return rc;
   IIF_CU(cudaEventRecord(s.step_done, p->s_compute));
   if (p->ar_on) {
     const int lane = p->ar_next;
@@ -109,8 +113,9 @@ extern "C" int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x
   if (!p || slot < 0 || slot >= p->nslots || !host_x || !host_label || !host_loss) return IIF_EINVAL;
   iif_pipeline::Slot& s = p->slots[slot];
   const iif_head_args& a = s.a;
-  // the slot's device buffers are free once its previous step (and whoever held its gradients) is done
-  if (s.used) IIF_CU(cudaStreamWaitEvent(p->s_h2d, s.loss_done, 0));
+  // the slot's device buffers are free once its previous step (and whoever held its gradients) is done -- nothing to
+  // enqueue when the host has already waited for that step (every driver call here is ~2 us of a ~25 us step)
+  if (s.used && !s.waited) IIF_CU(cudaStreamWaitEvent(p->s_h2d, s.direct_last ? s.step_done : s.loss_done, 0));
   if (a.ldx == a.D)
     IIF_CU(cudaMemcpyAsync(const_cast<void*>(a.x), host_x, (size_t)a.B * a.D * 2, cudaMemcpyHostToDevice, p->s_h2d));
   else
@@ -119,11 +124,29 @@ extern "C" int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x
   IIF_CU(cudaMemcpyAsync(const_cast<int64_t*>(a.label), host_label, (size_t)a.B * 8, cudaMemcpyHostToDevice, p->s_h2d));
   IIF_CU(cudaEventRecord(s.h2d_done, p->s_h2d));
   IIF_CU(cudaStreamWaitEvent(p->s_compute, s.h2d_done, 0));
-  if (int rc = run_step(p, s)) return rc;
-  IIF_CU(cudaStreamWaitEvent(p->s_d2h, s.step_done, 0));
-  IIF_CU(cudaMemcpyAsync(host_loss, a.loss_sum, 4, cudaMemcpyDeviceToHost, p->s_d2h));
-  IIF_CU(cudaEventRecord(s.loss_done, p->s_d2h));
+  // Loss read-back: when the caller's host word is pinned (device-addressable under unified addressing) the kernel's
+  // own 4-byte store delivers it -- no copy stream, no extra events; otherwise a D2H copy on the third stream.
+  if (s.direct_host != host_loss) {
+    s.direct_host = host_loss;
+    s.direct_dev = nullptr;
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, host_loss, 0) == cudaSuccess && dp) s.direct_dev = static_cast<float*>(dp);
+    else cudaGetLastError();
+    s.a_direct = s.a;
+    s.a_direct.loss_sum = s.direct_dev;
+  }
+  if (s.direct_dev) {
+    if (int rc = run_step(p, s, &s.a_direct)) return rc;        // (records step_done after the launch)
+    s.direct_last = true;
+  } else {
+    if (int rc = run_step(p, s)) return rc;
+    IIF_CU(cudaStreamWaitEvent(p->s_d2h, s.step_done, 0));
+    IIF_CU(cudaMemcpyAsync(host_loss, a.loss_sum, 4, cudaMemcpyDeviceToHost, p->s_d2h));
+    IIF_CU(cudaEventRecord(s.loss_done, p->s_d2h));
+    s.direct_last = false;
+  }
   s.used = true;
+  s.waited = false;
   s.device_only = false;
   return IIF_OK;
 }
@@ -132,6 +155,7 @@ extern "C" int iif_pipeline_submit(iif_pipeline* p, int slot, const void* host_x
 extern "C" int iif_pipeline_submit_device(iif_pipeline* p, int slot) {
   if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
   p->slots[slot].device_only = true;
+  p->slots[slot].waited = false;
   return run_step(p, p->slots[slot]);
 }
 
@@ -228,9 +252,54 @@ extern "C" int iif_pipeline_enable_staged(iif_pipeline* p) {
     IIF_CU(cudaGraphInstantiate(&s.exec, graph, 0));
     cudaGraphDestroy(graph);
   }
+  // The ring graph: one step of EVERY slot, in order, as one graph launch -- slot k's launch with the H2D of slot
+  // k + 1's staged batch as a parallel branch, each slot's loss event recorded as an external event node.  One driver
+  // call per `nslots` steps: the per-step graph-launch latency and the host's launch path leave the step time.
+  {
+    cudaGraph_t graph = nullptr;
+    IIF_CU(cudaStreamBeginCapture(p->s_compute, cudaStreamCaptureModeRelaxed));
+    int rc = copy_in(p, p->slots[0], p->s_compute);
+    int launches = 0;
+    for (int i = 0; i < p->nslots && !rc; ++i) {
+      iif_pipeline::Slot& s = p->slots[i];
+      const bool more = i + 1 < p->nslots;
+      if (more) {
+        if (cudaEventRecord(fork, p->s_compute) != cudaSuccess || cudaStreamWaitEvent(p->s_h2d, fork, 0) != cudaSuccess) rc = IIF_EDRIVER;
+        if (!rc) rc = copy_in(p, p->slots[i + 1], p->s_h2d);
+        if (!rc && cudaEventRecord(join, p->s_h2d) != cudaSuccess) rc = IIF_EDRIVER;
+      }
+      if (!rc) rc = iif_head_fwd_bwd_bf16(&s.a_staged, p->s_compute);
+      if (!rc && cudaEventRecordWithFlags(s.loss_done, p->s_compute, cudaEventRecordExternal) != cudaSuccess) rc = IIF_EDRIVER;
+      if (!rc && more && cudaStreamWaitEvent(p->s_compute, join, 0) != cudaSuccess) rc = IIF_EDRIVER;
+      launches += s.launches;
+    }
+    cudaError_t e = cudaStreamEndCapture(p->s_compute, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    IIF_CU(e);
+    IIF_CU(cudaGraphInstantiate(&p->ring_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    p->ring_launches = launches;
+  }
   cudaEventDestroy(fork);
   cudaEventDestroy(join);
   p->staged = true;
+  p->primed = -1;
+  return IIF_OK;
+}
+
+// One step of every slot (0 .. nslots-1, in order) from the slots' staging buffers, as ONE graph launch.  Contract:
+// every slot's staging holds its batch when this is called and is not rewritten before iif_pipeline_wait(slot)
+// returns for that slot (a data loader `nslots` batches ahead, refilling a slot once its loss has been read).
+extern "C" int iif_pipeline_submit_staged_ring(iif_pipeline* p) {
+  if (!p || !p->staged || !p->ring_exec) return IIF_EINVAL;
+  IIF_CU(cudaGraphLaunch(p->ring_exec, p->s_compute));
+  iif::g_launches.fetch_add((uint64_t)p->ring_launches, std::memory_order_relaxed);
+  for (int i = 0; i < p->nslots; ++i) {
+    p->slots[i].used = true;
+    p->slots[i].waited = false;
+    p->slots[i].device_only = false;
+    p->slots[i].direct_last = false;
+  }
   p->primed = -1;
   return IIF_OK;
 }
@@ -254,7 +323,9 @@ extern "C" int iif_pipeline_submit_staged(iif_pipeline* p, int slot) {
   iif::g_launches.fetch_add((uint64_t)s.launches, std::memory_order_relaxed);
   p->primed = (slot + 1) % p->nslots;
   s.used = true;
+  s.waited = false;
   s.device_only = false;
+  s.direct_last = false;
   return IIF_OK;
 }
 
@@ -262,7 +333,8 @@ extern "C" int iif_pipeline_wait(iif_pipeline* p, int slot) {
   if (!p || slot < 0 || slot >= p->nslots) return IIF_EINVAL;
   if (p->slots[slot].device_only) return IIF_EINVAL;   // submit_device copies no loss back: nothing to wait for
   if (!p->slots[slot].used) return IIF_OK;
-  IIF_CU(cudaEventSynchronize(p->slots[slot].loss_done));
+  IIF_CU(cudaEventSynchronize(p->slots[slot].direct_last ? p->slots[slot].step_done : p->slots[slot].loss_done));
+  p->slots[slot].waited = true;
   return IIF_OK;
 }
 
@@ -294,6 +366,7 @@ extern "C" void iif_pipeline_destroy(iif_pipeline* p) {
   for (int i = 0; i < p->nslots; ++i) {
     if (p->staged) {
       if (p->slots[i].exec) cudaGraphExecDestroy(p->slots[i].exec);
+      if (i == 0 && p->ring_exec) cudaGraphExecDestroy(p->ring_exec);
       cudaFreeHost(p->slots[i].host_x);
       cudaFreeHost(p->slots[i].host_y);
       cudaFreeHost(p->slots[i].host_loss);

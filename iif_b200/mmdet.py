@@ -269,7 +269,7 @@ class Linear(nn.Linear):
 
     def __init__(self, *args, compute="bf16", **kwargs):
         super().__init__(*args, **kwargs)
-        assert compute in ("bf16", "fp32")
+        assert compute in ("bf16", "fp32", "fp32x3")
         self.compute = compute
         self._w16 = None
         self._w16_key = None
@@ -291,7 +291,7 @@ class Linear(nn.Linear):
     def forward(self, x):
         if self.compute == "bf16":
             return F_.linear(x, self.weight, self.bias, bf16=True, weight_bf16=self.weight_bf16())
-        return F_.linear(x, self.weight, self.bias, bf16=False)
+        return F_.linear(x, self.weight, self.bias, bf16="x3" if self.compute == "fp32x3" else False)
 
 
 class NormedLinear(Linear):
@@ -335,6 +335,18 @@ class IIFNormedLinear(NormedLinear):
 
     def _class_scale(self):
         return self.iif_weights.reshape(-1)
+
+
+def sibling_forward(fc_cls, fc_reg, x):
+    """`cls_score = self.fc_cls(x); bbox_pred = self.fc_reg(x)` of BBoxHead.forward (bbox_head.py:118-119,
+    convfc_bbox_head.py:188-189) as ONE GEMM per direction over the shared RoI features.  `fc_cls` / `fc_reg` stay
+    two nn.Linear modules (checkpoint names, init_cfg overrides and `selectp` keep working); a normalised fc_cls
+    (NormedLinear / IIFNormedLinear) or the fp32 parity mode falls back to the two separate calls."""
+    plain = type(fc_cls) in (Linear, nn.Linear) and type(fc_reg) in (Linear, nn.Linear)
+    if not plain or getattr(fc_cls, "compute", "bf16") != "bf16" or getattr(fc_reg, "compute", "bf16") != "bf16" \
+            or not x.is_cuda or x.numel() == 0:
+        return fc_cls(x), fc_reg(x)
+    return F_.sibling_linear(x, fc_cls.weight, fc_cls.bias, fc_reg.weight, fc_reg.bias)
 
 
 def register_all():

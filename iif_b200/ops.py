@@ -133,6 +133,12 @@ def weights_from_counts(counts: torch.Tensor, variant: str, total: int = 0, norm
 # ------------------------------------------------------------------------------------------------
 # loss kernels
 # ------------------------------------------------------------------------------------------------
+def pad64(n: int) -> int:
+    """Row pitch (elements) of a bf16 matrix whose rows start on 128-byte boundaries: TMA boxes are 128 bytes wide
+    and a row that straddles two 128-byte lines costs two L2 requests per box row."""
+    return (int(n) + 63) // 64 * 64
+
+
 def pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -337,11 +343,16 @@ def shot_accuracy(preds, labels, train_counts, many_shot_thr=100, low_shot_thr=2
     return (out3, test, correct, cacc) if want_class_acc else (out3, test, correct)
 
 
-def scale_rows(x, g=None, *, bf16=False, pad_ld=False):
-    """x[rows, cols] fp32 * g (None | 0-dim device scalar | [rows]) -> fp32 or bf16 (optionally ld padded to 8)."""
+def scale_rows(x, g=None, *, bf16=False, pad_ld=False, out=None):
+    """x[rows, cols] fp32 * g (None | 0-dim device scalar | [rows]) -> fp32 or bf16 (optionally ld padded to 8).
+    `out`: write into this [rows, cols] view (unit inner stride, any leading dimension) instead of allocating."""
     x = _rows(x, "x", torch.float32)
     rows, cols = x.shape
     dev = x.device
+    if out is not None:
+        _cuda(out, "out", torch.bfloat16 if bf16 else torch.float32)
+        if tuple(out.shape) != (rows, cols) or (cols > 1 and out.stride(1) != 1):
+            raise ValueError(f"iif_b200: scale_rows out must be [{rows},{cols}] with unit inner stride")
     gs = 0
     if g is not None:
         g = _cuda(g, "g")
@@ -349,13 +360,17 @@ def scale_rows(x, g=None, *, bf16=False, pad_ld=False):
         if g.numel() not in (1, rows):
             raise ValueError("g must be a scalar or have one entry per row")
         gs = 0 if g.numel() == 1 and rows != 1 else (1 if g.numel() == rows and rows > 1 else 0)
-    ldo = pad8(cols) if (bf16 and pad_ld) else cols
-    out = torch.empty(rows, ldo, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
+    if out is not None:
+        ldo, ret = _ld(out), out
+    else:
+        ldo = pad8(cols) if (bf16 and pad_ld) else cols
+        out = torch.empty(rows, ldo, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
+        ret = out if ldo == cols else out[:, :cols]
     if rows and cols:
         _lib.check(_lib.load().iif_scale_rows(_ptr(x), _ld(x), _ptr(g), gs, rows, cols, _ptr(out),
                                               _lib.DTYPE_BF16 if bf16 else _lib.DTYPE_F32, ldo, _stream(dev)),
                    "scale_rows")
-    return out if ldo == cols else out[:, :cols]
+    return ret
 
 
 def row_scale_from_norm(x, mode, *, pre=None, temperature=1.0, power=1.0, eps=1e-6, want_c=True):
@@ -399,6 +414,32 @@ def rows_axpby(u, a=None, v=None, b=None, b2=None):
     if rows and cols:
         _lib.check(_lib.load().iif_rows_axpby(_ptr(u), _ld(u), _ptr(a), _ptr(v), 0 if v is None else _ld(v), _ptr(b),
                                               _ptr(b2), rows, cols, _ptr(out), cols, _stream(dev)), "rows_axpby")
+    return out
+
+
+def scale_inplace_(t, g):
+    """t *= g (0-dim / 1-element fp32 device tensor) in place; a no-op launch when g == 1."""
+    _cuda(t, "t")
+    _cuda(g, "g", torch.float32)
+    if t.dtype not in (torch.float32, torch.bfloat16) or not t.is_contiguous():
+        raise TypeError("iif_b200: scale_inplace_ takes a contiguous fp32 / bf16 tensor")
+    _lib.check(_lib.load().iif_scale_inplace(_ptr(t), _lib.DTYPE_BF16 if t.dtype == torch.bfloat16 else _lib.DTYPE_F32,
+                                             t.numel(), _ptr(g.reshape(1)), _stream(t.device)), "scale_inplace")
+    return t
+
+
+def split3(x, *, k_along_rows: bool, side_b: bool):
+    """fp32 [rows, cols] -> the six-copy bf16 expansion along the contraction dimension (csrc/split3.cu):
+    [rows, 6 * pad8(cols)] (K along columns) or [6 * pad8(rows), pad8-pitched cols] (K along rows)."""
+    x = _rows(x, "x", torch.float32)
+    rows, cols = x.shape
+    if k_along_rows:
+        out = torch.empty(6 * pad8(rows), pad8(cols), dtype=torch.bfloat16, device=x.device)[:, :cols]
+    else:
+        out = torch.empty(rows, 6 * pad8(cols), dtype=torch.bfloat16, device=x.device)
+    if rows and cols:
+        _lib.check(_lib.load().iif_split3_bf16(_ptr(x), _ld(x), rows, cols, int(bool(k_along_rows)), int(bool(side_b)),
+                                               _ptr(out), int(out.stride(0)), _stream(x.device)), "split3_bf16")
     return out
 
 
@@ -541,14 +582,14 @@ class HeadStep:
     (`grad_flat`) so the data-parallel all-reduce of the head's parameter gradients is one message."""
 
     def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, want_acc=False, ws=None,
-                 fused_loss=True, grad_flat=None, persistent=True):
+                 fused_loss=True, grad_flat=None, persistent=True, scratch=None):
         dev = torch.device(device)
         self.B, self.D, self.C, self.device = B, D, Cc, dev
         f32, i32 = torch.float32, torch.int32
         self.z = torch.empty(B, Cc, dtype=f32, device=dev)
         self.loss_i = torch.empty(B, dtype=f32, device=dev)
         self.loss = torch.zeros((), dtype=f32, device=dev)
-        self.dz = torch.empty(B, pad8(Cc), dtype=torch.bfloat16, device=dev)
+        self.dz = torch.empty(B, pad64(Cc), dtype=torch.bfloat16, device=dev)
         self.dx = torch.empty(B, D, dtype=torch.bfloat16 if dx_bf16 else f32, device=dev) if need_dx else None
         ng = Cc * D + (Cc if need_db else 0)
         if grad_flat is not None:      # caller-owned storage (e.g. a peer-mapped buffer of parallel.PeerAllReduce)
@@ -560,7 +601,8 @@ class HeadStep:
         self.argmax = torch.empty(B, dtype=i32, device=dev) if want_acc else None
         self.rank = torch.empty(B, dtype=i32, device=dev) if want_acc else None
         self.acc_counts = torch.zeros(2, dtype=i32, device=dev) if want_acc else None
-        self.scratch = torch.zeros((int(_lib.load().iif_loss_scratch_bytes(B)) + 3) // 4, dtype=i32, device=dev)
+        self.scratch = scratch if scratch is not None else \
+            torch.zeros((int(_lib.load().iif_loss_scratch_bytes(B)) + 3) // 4, dtype=i32, device=dev)
         n = int(_lib.load().iif_gemm_ws_bytes(B, D, Cc))
         if ws is not None and ws.numel() < n:
             raise ValueError("HeadStep: shared workspace too small")
@@ -654,6 +696,74 @@ class HeadStep:
             p(a.dz_bf16), a.lddz, p(a.x), a.ldx, p(a.w), a.ldw, None, p(a.dx), a.dx_dtype, a.lddx, p(a.dw), a.lddw,
             p(a.db), a.B, a.D, a.C, p(a.ws), a.ws_bytes, st())))
         return out
+
+class SigmoidHeadStep:
+    """The head step in SIGMOID mode (mmdet CrossEntropyLoss(use_sigmoid=True) / FasaIIFLoss(use_sigmoid=True) as
+    loss_cls, seg/mmdet/models/losses/cross_entropy_loss.py:74-111; no IIF scale in this mode, fasa_iif_loss.py:35-36):
+    fc_cls GEMM -> sigmoid-BCE fwd+bwd (bf16 dZ, no one-hot tensor) -> dX, dW, db in one grouped launch -- three
+    launches on pre-allocated buffers, same layout as `HeadStep` (flat [dW | db] gradient buffer)."""
+
+    def __init__(self, B, D, Cc, device, *, need_dx=True, dx_bf16=True, need_db=True, grad_flat=None, ws=None):
+        dev = torch.device(device)
+        self.B, self.D, self.C, self.device = B, D, Cc, dev
+        f32 = torch.float32
+        self.z = torch.empty(B, Cc, dtype=f32, device=dev)
+        self.loss_i = torch.empty(B, dtype=f32, device=dev)
+        self.loss = torch.zeros((), dtype=f32, device=dev)
+        self.dz = torch.empty(B, pad64(Cc), dtype=torch.bfloat16, device=dev)
+        self.dz[:, Cc:].zero_()
+        self.dx = torch.empty(B, D, dtype=torch.bfloat16 if dx_bf16 else f32, device=dev) if need_dx else None
+        ng = Cc * D + (Cc if need_db else 0)
+        self.grad_flat = grad_flat if grad_flat is not None else torch.empty(ng, dtype=f32, device=dev)
+        self.dw = self.grad_flat[:Cc * D].view(Cc, D)
+        self.db = self.grad_flat[Cc * D:] if need_db else None
+        self.scratch = torch.zeros((int(_lib.load().iif_loss_scratch_bytes(B)) + 3) // 4, dtype=torch.int32, device=dev)
+        n = int(_lib.load().iif_gemm_ws_bytes(B, D, Cc))
+        self.ws = ws if ws is not None else torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
+        self.ws_bytes = n
+        self.dx_dtype = _lib.DTYPE_BF16 if dx_bf16 else _lib.DTYPE_F32
+        self.launches_per_step = 3
+
+    def bind(self, x, w, bias, label, *, pos_weight=None, sample_weight=None, ignore_index=-100, scale=None):
+        B, D, Cc = self.B, self.D, self.C
+        _cuda(x, "x", torch.bfloat16)
+        _cuda(w, "w", torch.bfloat16)
+        _cuda(label, "label", torch.int64)
+        if tuple(x.shape) != (B, D) or tuple(w.shape) != (Cc, D) or label.numel() != B:
+            raise ValueError("SigmoidHeadStep: shape mismatch")
+        self._bias = _vec(bias, "bias", Cc)
+        self._pw = _vec(pos_weight, "pos_weight", Cc)
+        self._sw = _vec(sample_weight, "sample_weight", B)
+        self._x, self._w, self._y = x, w, label
+        self._ign = int(ignore_index)
+        self._scale = float(1.0 / (B * Cc) if scale is None else scale)      # 'mean' over B*C elements
+        return self
+
+    def kernels(self):
+        lib, p = _lib.load(), C.c_void_p
+        st = lambda: _stream(self.device)
+        B, D, Cc = self.B, self.D, self.C
+        x, w, y = self._x, self._w, self._y
+        return [
+            ("linear_fwd_bf16", lambda: lib.iif_linear_fwd_bf16(p(x.data_ptr()), x.stride(0), p(w.data_ptr()), w.stride(0),
+                                                                _ptr(self._bias), None, _ptr(self.z), Cc, None, 0, B, D, Cc,
+                                                                _ptr(self.ws), self.ws_bytes, st())),
+            ("sigmoid_bce_fwd_bwd", lambda: lib.iif_sigmoid_bce_fwd_bwd(
+                _ptr(self.z), Cc, _ptr(y), _ptr(self._pw), None, _ptr(self._sw), self._ign, self._scale, B, Cc, None, 0,
+                _ptr(self.loss_i), _ptr(self.loss), None, 0, _ptr(self.dz), self.dz.stride(0), _ptr(self.scratch), st())),
+            ("linear_bwd_bf16", lambda: lib.iif_linear_bwd_bf16(
+                _ptr(self.dz), self.dz.stride(0), p(x.data_ptr()), x.stride(0), p(w.data_ptr()), w.stride(0), None,
+                _ptr(self.dx), self.dx_dtype, D, _ptr(self.dw), D, _ptr(self.db), B, D, Cc, _ptr(self.ws), self.ws_bytes,
+                st())),
+        ]
+
+    def launch(self):
+        for name, fn in self.kernels():
+            rc = fn()
+            if rc:
+                _lib.check(rc, name)
+        return self.loss
+
 
 class HeadPipeline:
     """Host-batch pipeline over bound `HeadStep` slots (C: iif_pipeline_*, csrc/pipeline.cu).
@@ -750,6 +860,14 @@ class HeadPipeline:
         if rc:
             _lib.check(rc, "pipeline_submit_staged")
         self._staged_last[slot] = True
+
+    def submit_staged_ring(self) -> None:
+        """One step of every slot, in order, from the staging buffers: ONE graph launch for len(steps) steps."""
+        rc = self._lib.iif_pipeline_submit_staged_ring(self._h)
+        if rc:
+            _lib.check(rc, "pipeline_submit_staged_ring")
+        for k in range(len(self.steps)):
+            self._staged_last[k] = True
 
     def wait(self, slot: int) -> float:
         rc = self._lib.iif_pipeline_wait(self._h, slot)

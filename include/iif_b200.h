@@ -222,6 +222,10 @@ IIF_API int iif_shot_accuracy(const int32_t* preds, const int64_t* labels, int64
 IIF_API int iif_scale_rows(const float* in, int64_t ldi, const float* g, int64_t g_stride, int64_t rows,
                    int64_t cols, void* out, int out_dtype, int64_t ldo, void* stream);
 
+/* data[0..n) *= *g_dev in place (fp32 or bf16 storage); a no-op launch when *g_dev == 1.  Applies the upstream scalar
+ * of autograd to gradients that the one-launch head step already formed in the forward call. */
+IIF_API int iif_scale_inplace(void* data, int dtype, int64_t n, const float* g_dev, void* stream);
+
 /* db[c] = alpha * sum_i dz[i,c]   (alpha_dev == NULL -> 1; fixed-order, deterministic).
  * The bias gradient of AddmmBackward (a10). */
 IIF_API int iif_colsum(const void* dz, int dz_dtype, int64_t lddz, const float* alpha_dev, int64_t rows,
@@ -267,6 +271,16 @@ IIF_API int iif_linear_fwd_bf16(const void* x, int64_t ldx, const void* w, int64
 IIF_API int iif_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
                        const float* col_scale, float* z, int64_t ldz, float* zs, int64_t ldzs,
                        int64_t B, int64_t D, int64_t C, void* stream);
+
+/* fp32 parity mode on the tensor cores: expand an fp32 operand into six bf16 copies along the contraction dimension
+ * (v = v_h + v_m + v_l; A side: h h m h m l, B side: h m h l m h) so that ONE call of the bf16 GEMM entry points above /
+ * below with a six times longer K forms  A_h B_h + A_h B_m + A_m B_h + A_h B_l + A_m B_m + A_l B_h  in fp32 -- the
+ * product to ~2^-24 relative, i.e. within the 1e-5 bar, at tensor-core speed (csrc/split3.cu).
+ *   k_along_rows = 0: in [rows, cols] -> out [rows, 6 * pad8(cols)] (copy k at column k * pad8(cols); padding zero)
+ *   k_along_rows = 1: in [rows, cols] -> out [6 * pad8(rows), cols] (copy k at row k * pad8(rows); padding zero)
+ *   side_b: 0 = the A operand's term order, 1 = the B operand's. */
+IIF_API int iif_split3_bf16(const float* in, int64_t ldi, int64_t rows, int64_t cols, int k_along_rows, int side_b,
+                    void* out, int64_t ldo, void* stream);
 
 /* dX[B,D] = alpha * dZ[B,C] W[C,D]   (AddmmBackward, a10).  alpha_dev: device scalar or NULL. */
 IIF_API int iif_linear_bwd_dx_bf16(const void* dz, int64_t lddz, const void* w, int64_t ldw,
@@ -404,6 +418,11 @@ IIF_API int iif_pipeline_get_streams(iif_pipeline* p, void** h2d, void** compute
 IIF_API int iif_pipeline_enable_staged(iif_pipeline* p);
 IIF_API int iif_pipeline_staging(iif_pipeline* p, int slot, void** host_x, int64_t** host_label, float** host_loss);
 IIF_API int iif_pipeline_submit_staged(iif_pipeline* p, int slot);
+/* One step of EVERY slot (0 .. nslots-1, in order) from the slots' staging buffers as ONE graph launch: slot k's
+ * launch with the H2D of slot k+1's staged batch as a parallel branch, each slot's loss event an external event node
+ * (iif_pipeline_wait(slot) works per slot).  One driver call per nslots steps.  Contract: every slot's staging holds
+ * its batch at the call and is not rewritten until iif_pipeline_wait(slot) has returned for that slot. */
+IIF_API int iif_pipeline_submit_staged_ring(iif_pipeline* p);
 /* Block until the slot's latest step has delivered its loss to host_loss. */
 IIF_API int iif_pipeline_wait(iif_pipeline* p, int slot);
 /* Make `stream` wait for the slot's latest step (its gradients are then complete) ... */

@@ -349,7 +349,7 @@ def class_accumulate(label, loss, num_bins, cum_losses=None, cum_labels=None):
     """fasa_iif_loss.py:154-160: for u in label.unique(): cum_labels[int(u)] += #rows, cum_losses[int(u)] +=
     loss[rows].sum() -- python indexing, so a negative label counts from the end; [B,C] losses sum their rows."""
     y = np.asarray(label, np.int64).reshape(-1)
-    l = np.asarray(loss, np.float64).reshape(y.shape[0], -1).sum(1)
+    l = np.asarray(loss, np.float64).reshape(y.shape[0], -1).sum(1) if y.shape[0] else np.zeros(0)
     cl = np.zeros(num_bins) if cum_losses is None else np.array(cum_losses, np.float64)
     cn = np.zeros(num_bins) if cum_labels is None else np.array(cum_labels, np.float64)
     for u in np.unique(y):

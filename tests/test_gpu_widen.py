@@ -171,3 +171,48 @@ def test_class_feature_stats(golden):
     ops.class_feature_stats(T(x), T(y), mean, var, used, 0.1)
     rm, rv, ru = ho.class_feature_stats(x, y, m0, v0, u0, 0.1)
     assert rel_err(N(mean), rm) < TOL_F32 and rel_err(N(var), rv) < 2e-5 and np.array_equal(N(used), ru)
+
+
+@pytest.mark.parametrize("B,D,C1,C2", [(1024, 1024, 1204, 4812), (77, 520, 9, 36), (512, 256, 81, 320)])
+def test_sibling_fc_cls_fc_reg(B, D, C1, C2):
+    """fc_cls + fc_reg on the same RoI features (bbox_head.py:118-119): one GEMM per direction, same results as the two
+    separate layers / the oracle on bf16-rounded operands."""
+    from iif_b200 import mmdet as M
+    from _common import bf16_round
+    rng = np.random.default_rng(B + C1)
+    x = np.maximum(rng.standard_normal((B, D)), 0).astype(np.float32)
+    fc_cls, fc_reg = M.Linear(D, C1).to(DEV), M.Linear(D, C2).to(DEV)
+    xt = T(x).requires_grad_(True)
+    zc, zr = M.sibling_forward(fc_cls, fc_reg, xt)
+    gc, gr = rng.standard_normal((B, C1)).astype(np.float32) / B, rng.standard_normal((B, C2)).astype(np.float32) / B
+    (zc * T(gc)).sum().backward(retain_graph=True)
+    (zr * T(gr)).sum().backward()
+    wc, wr = N(fc_cls.weight), N(fc_reg.weight)
+    xb = bf16_round(x)
+    for z, w, b in ((zc, wc, N(fc_cls.bias)), (zr, wr, N(fc_reg.bias))):
+        assert rel_err(N(z), ho.linear_fwd(xb, bf16_round(w.astype(np.float32)), b)) < 2e-5
+    dxc, dwc, dbc = ho.linear_bwd(bf16_round(gc), xb, bf16_round(wc.astype(np.float32)))
+    dxr, dwr, dbr = ho.linear_bwd(bf16_round(gr), xb, bf16_round(wr.astype(np.float32)))
+    assert rel_err(N(xt.grad), dxc + dxr) < 1e-2
+    assert rel_err(N(fc_cls.weight.grad), dwc) < 1e-2 and rel_err(N(fc_reg.weight.grad), dwr) < 1e-2
+    assert rel_err(N(fc_cls.bias.grad), dbc) < 1e-2 and rel_err(N(fc_reg.bias.grad), dbr) < 1e-2
+
+
+@pytest.mark.parametrize("B,D,C", [(256, 2048, 1000), (128, 64, 10), (77, 520, 1203), (1024, 1024, 1204)])
+def test_fp32_parity_on_tensor_cores(B, D, C):
+    """compute='fp32x3': fp32 operands split into three bf16 terms, six partial products on the tensor cores, fp32
+    accumulation -- forward and gradients within the 1e-5 bar of the float64 oracle (csrc/split3.cu)."""
+    from iif_b200 import mmdet as M
+    from _common import head_inputs
+    x, w, b, counts, y = head_inputs(B, D, C, seed=7)
+    fc = M.Linear(D, C, compute="fp32x3").to(DEV)
+    with torch.no_grad():
+        fc.weight.copy_(T(w)); fc.bias.copy_(T(b))
+    xt = T(x).requires_grad_(True)
+    z = fc(xt)
+    gz = np.random.default_rng(1).standard_normal((B, C)).astype(np.float32) / B
+    z.backward(T(gz))
+    assert rel_err(N(z), ho.linear_fwd(x, w, b)) < TOL_F32
+    dx, dw, db = ho.linear_bwd(gz, x, w)
+    assert rel_err(N(xt.grad), dx) < TOL_F32 and rel_err(N(fc.weight.grad), dw) < TOL_F32
+    assert rel_err(N(fc.bias.grad), db) < TOL_F32

@@ -11,7 +11,8 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 numel = int(sys.argv[1]) if len(sys.argv) > 1 else 1000 * 2048 + 1000
 ok = True
-CFG = [(True, 0, 0), (False, 0, 0)] + ([(True, 40, 256), (False, 40, 256), (True, 40, 512), (True, 64, 128)] if os.environ.get("AR_SWEEP") else [])
+CFG = [(True, 0, 0), (False, 0, 0)] + ([(True, 32, 256), (True, 64, 256), (True, 148, 256), (True, 148, 128), (True, 148, 64),
+                                        (False, 148, 256)] if os.environ.get("AR_SWEEP") else [])
 for mc, nct, nth in CFG:
     try:
         par = PeerAllReduce(numel, 4, dev, use_multicast=mc, num_ctas=nct, num_threads=nth)
@@ -61,7 +62,7 @@ for mc, nct, nth in CFG:
     # phase timeline of one call (globaltimer stamps of every CTA)
     from iif_b200 import _lib
     import numpy as np
-    dbg = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(192 * 8, dtype=torch.int64, device=dev)
     torch.cuda.synchronize(); dist.barrier()
     _lib.load().iif_debug_timing_allreduce(dbg.data_ptr())
     par.all_reduce(0, st)
