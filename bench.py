@@ -37,6 +37,10 @@ import sys
 import threading
 import time
 
+# more hardware work queues than the default 8: the pipeline's compute / copy / comm-lane streams (plus torch's and
+# NCCL's) must not alias one another, or two all-reduce lanes serialise behind each other
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

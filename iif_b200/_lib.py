@@ -16,6 +16,7 @@ VARIANT_IDS = {"raw": 0, "smooth": 1, "rel": 2, "prob": 2, "normit": 3, "gombit"
 DTYPE_F32, DTYPE_BF16 = 0, 1
 HEAD_NO_FUSED_LOSS = 1
 HEAD_NO_PERSISTENT = 2
+HEAD_LOW_REGS = 4
 NORM_NORMED, NORM_COS, NORM_UNIT = 0, 1, 2
 
 _p, _i64, _i32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t

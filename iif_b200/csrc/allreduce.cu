@@ -50,11 +50,15 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 __device__ __forceinline__ void ar_barrier(uint32_t* const* flags, size_t lane_off, int rank, int world, uint32_t value,
-                                           bool release, unsigned long long timeout_ns) {
+                                           int release, unsigned long long timeout_ns) {
   __syncthreads();
   const size_t slot = lane_off + (size_t)blockIdx.x * AR_MAX_WORLD;
   if (threadIdx.x == 0) {
-    if (release) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    // release == 1: system scope (remote stores must have landed).  release == 2: gpu scope -- enough when the data
+    // being published are LOCAL stores that peers will read over NVLink: peer reads are served by this GPU's L2, the
+    // point a gpu-scope fence orders the CTA's stores to; the system-scope fence costs ~7 us even then.
+    if (release == 1) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else if (release == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
     for (int p = 0; p < world; ++p)
       asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flags[p] + slot + rank), "r"(value) : "memory");
   }
@@ -119,7 +123,7 @@ allreduce_mean_kernel(float* const* bufs, uint32_t* const* flags, float* mc, int
   // launch number of this CTA (stream-ordered launches: no race), stored next to the flags
   uint32_t* epoch_p = flags[rank] + lane_off + (size_t)AR_MAX_CTAS * AR_MAX_WORLD + blockIdx.x;
   const uint32_t epoch = *epoch_p + 1;
-  ar_barrier(flags, lane_off, rank, world, 2 * epoch, false, timeout_ns);
+  ar_barrier(flags, lane_off, rank, world, 4 * epoch, 0, timeout_ns);
   if (threadIdx.x == 0) *epoch_p = epoch;
   ar_stamp(dbg, 1);
   const int64_t per = (n4 + world - 1) / world;                    // float4 per rank slice
@@ -173,8 +177,109 @@ allreduce_mean_kernel(float* const* bufs, uint32_t* const* flags, float* mc, int
     }
   }
   ar_stamp(dbg, 2);
-  ar_barrier(flags, lane_off, rank, world, 2 * epoch + 1, true, timeout_ns);            // release: our peer stores land before the "done" flag
+  ar_barrier(flags, lane_off, rank, world, 4 * epoch + 2, 1, timeout_ns);               // release: our peer stores land before the "done" flag
   ar_stamp(dbg, 3);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pull form (round 2): NO remote stores, hence no system-scope fence that waits for remote write acknowledgements --
+// the closing cost of the push form above (8 us at 2 GPUs, 17 us at 8).
+//   open : cross-rank barrier ("my gradients are final")
+//   1    : rank r reduces ITS slice (multimem.ld_reduce, or peer loads summed in rank order), scales it and stores the
+//          result into its OWN buffer -- local stores only
+//   mid  : barrier with a system-scope release of those local stores ("my slice is reduced")
+//   2    : every rank PULLS the other ranks' reduced slices with plain peer loads (flow-controlled by the loads
+//          themselves; CTA b reads exactly what CTA b of the owner wrote, so per-CTA flags suffice) and stores them
+//          locally
+//   close: barrier ("I have finished reading your buffer": it may be overwritten again)
+// In-bound NVLink traffic per GPU is the same (world-1)/world of the buffer; out-bound traffic is loads' replies only.
+// ------------------------------------------------------------------------------------------------------------------
+// Two geometries, both sized so that all-reduce CTAs are CO-RESIDENT with a CTA of the step kernel they overlap:
+//   <256 threads, <= 80 registers>  = 20 K registers: one all-reduce next to the 168-register step kernel;
+//   <128 threads, <= 128 registers> = 16 K registers: TWO all-reduces (two lanes in flight) next to the 128-register
+//                                     variant of the step kernel (IIF_HEAD_LOW_REGS) -- 32 K + 2 x 16 K = the SM's file.
+template <bool MULTICAST, int U, int TH, int MINB>
+__global__ void __launch_bounds__(TH, MINB)
+allreduce_pull_kernel(float* const* bufs, uint32_t* const* flags, float* mc, int rank, int world, int64_t n4,
+                      int64_t off4, int lane, long long* dbg, unsigned long long timeout_ns, int mid_fence) {
+  ar_stamp(dbg, 0);
+  const size_t lane_off = (size_t)lane * AR_LANE_WORDS;
+  uint32_t* epoch_p = flags[rank] + lane_off + (size_t)AR_MAX_CTAS * AR_MAX_WORLD + blockIdx.x;
+  const uint32_t epoch = *epoch_p + 1;
+  ar_barrier(flags, lane_off, rank, world, 4 * epoch, 0, timeout_ns);
+  if (threadIdx.x == 0) *epoch_p = epoch;
+  ar_stamp(dbg, 1);
+  const int64_t per = (n4 + world - 1) / world;                    // float4 per rank slice
+  const float inv = 1.f / (float)world;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float* mine = bufs[rank];
+  {  // ---- phase 1: my slice
+    const int64_t begin = rank * per, end = begin + per < n4 ? begin + per : n4;
+    for (int64_t i0 = begin + tid; i0 < end; i0 += stride * U) {
+      float4 acc[U];
+      if constexpr (MULTICAST) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (i0 + u * stride < end) acc[u] = mc_ld_reduce4(mc + (off4 + i0 + u * stride) * 4);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; ++p) {                            // rank order: the same sum everywhere, every run
+          float4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (i0 + u * stride < end) v[u] = ld_peer4(bufs[p] + (off4 + i0 + u * stride) * 4);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (i0 + u * stride < end) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + u * stride < end) {
+          acc[u].x *= inv; acc[u].y *= inv; acc[u].z *= inv; acc[u].w *= inv;
+          *reinterpret_cast<float4*>(mine + (off4 + i0 + u * stride) * 4) = acc[u];
+        }
+    }
+  }
+  ar_stamp(dbg, 2);
+  ar_barrier(flags, lane_off, rank, world, 4 * epoch + 1, mid_fence, timeout_ns);   // release: my LOCAL stores
+  ar_stamp(dbg, 3);
+  // ---- phase 2: pull the other ranks' slices.  A thread owns the SAME in-slice offsets o = tid + n * stride in every
+  // slice (the owner's phase-1 mapping: CTA b reads exactly what CTA b of the owner wrote, which is what makes the
+  // per-CTA barriers sufficient -- an earlier version flattened over all foreign elements instead, read other CTAs'
+  // elements and failed the 8-GPU stress check); its work list is the (offset, peer) pairs, U of them in flight, so the
+  // pull is a couple of NVLink round trips whatever the world size.  Each rank starts with a different peer.
+  {
+    const int nper = (int)((per + stride - 1) / stride);
+    const int total = nper * (world - 1);
+    for (int q0 = 0; q0 < total; q0 += U) {
+      float4 v[U];
+      int64_t idx[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = q0 + u;
+        idx[u] = -1;
+        if (q < total) {
+          const int n = q / (world - 1), k = q - n * (world - 1);
+          const int64_t o = tid + (int64_t)n * stride;
+          const int p = (rank + 1 + k) % world;
+          const int64_t i = p * per + o;
+          if (o < per && i < n4) {
+            idx[u] = i;
+            v[u] = ld_peer4(bufs[p] + (off4 + i) * 4);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (idx[u] >= 0) *reinterpret_cast<float4*>(mine + (off4 + idx[u]) * 4) = v[u];
+    }
+  }
+  ar_stamp(dbg, 4);
+  ar_barrier(flags, lane_off, rank, world, 4 * epoch + 2, 0, timeout_ns);      // nobody still reads my buffer
+  ar_stamp(dbg, 5);
 }
 
 }  // namespace iif
@@ -212,7 +317,7 @@ extern "C" int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* p
   if (lane < 0 || lane >= AR_LANES) return IIF_EINVAL;
   if (n_elems < 0 || offset_elems < 0 || (n_elems & 3) || (offset_elems & 3)) return IIF_EALIGN;
   if (n_elems == 0) return IIF_OK;
-  if (num_ctas <= 0) num_ctas = 16;
+  if (num_ctas <= 0) num_ctas = kNumSMs;           // one light CTA per SM, next to the step kernel's CTA
   if (num_ctas > AR_MAX_CTAS) num_ctas = AR_MAX_CTAS;
   if (num_threads <= 0) num_threads = 256;
   if (num_threads > AR_THREADS || (num_threads & 31) || num_threads < 32) return IIF_EINVAL;
@@ -222,6 +327,26 @@ extern "C" int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* p
   float* mc = reinterpret_cast<float*>(multicast_ptr);
   const int64_t n4 = n_elems / 4, off4 = offset_elems / 4;
   const unsigned long long tmo = ar_timeout_ns();
+  // Form: measured (profiles/r2_multigpu.md) the pull form wins at 2 GPUs (28 us vs 36 us: no system-scope fence), the
+  // one-pass push form with in-switch reduction + multicast stores from 4 GPUs on (33 us vs 49 us at 8: NVLS broadcasts
+  // one slice to seven peers for one store, a pull moves seven slices as point-to-point loads).
+  // IIF_B200_AR_ALGO=pull|push overrides.
+  static const int algo = [] { const char* e = getenv("IIF_B200_AR_ALGO");
+                               return !e ? 0 : ((e[0] == 'p' && e[1] == 'u' && e[2] == 'l') ? 1 : ((e[0] == 'p' && e[1] == 'u' && e[2] == 's') ? 2 : 0)); }();
+  const bool pull = algo == 1 || (algo == 0 && (world <= 2 || !mc));
+  if (pull) {
+    static const int mid_fence = [] { const char* e = getenv("IIF_B200_AR_MIDFENCE"); return (e && e[0] == 's') ? 1 : 2; }();
+    // in-switch reduction pays from 4 ranks on: at 2 ranks multimem.ld_reduce moves 340 GB/s where two plain peer
+    // loads + an add move 610 GB/s (measured, profiles/r2_multigpu.md)
+    if (num_threads <= 128) {
+      if (mc && world >= 4) allreduce_pull_kernel<true, 16, 128, 4><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo, mid_fence);
+      else allreduce_pull_kernel<false, 8, 128, 4><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo, mid_fence);
+    } else {
+      if (mc && world >= 4) allreduce_pull_kernel<true, 8, 256, 3><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo, mid_fence);
+      else allreduce_pull_kernel<false, 4, 256, 3><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo, mid_fence);
+    }
+    return launch_status();
+  }
   if (mc) allreduce_mean_kernel<true, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo);
   else if (world <= 2) allreduce_mean_kernel<false, 8><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo);
   else if (world <= 4) allreduce_mean_kernel<false, 4><<<num_ctas, num_threads, 0, st>>>(bufs, flags, mc, rank, world, n4, off4, lane, g_ar_dbg, tmo);

@@ -221,18 +221,21 @@ __device__ __forceinline__ void load_logits(const Args& g, int64_t row, bool act
 }
 
 // dX = sum over splits of the parked partial tiles: U chunks of 256 float4 (8 rows of one tile) per pass.
+// The chunks are dealt to the `workers` CTAs that ran FEWER backward items than the busiest ones (rank `wrank` among
+// them; everybody when the items divide evenly): the busiest CTAs are the launch's critical path and go straight to
+// the exit, the others would idle.  Static and deterministic -- no work-stealing atomics.
 template <int U, int SMAX>
-__device__ __forceinline__ void reduce_dx(const Args& g, const int* ctrs) {
+__device__ __forceinline__ void reduce_dx(const Args& g, const int* ctrs, int wrank, int workers) {
   const int S = g.dx.splits;
   const int nchunks = g.dx.tiles_m * g.dx.tiles_n * 16;
-  const int G = (int)gridDim.x;
-  for (int c0 = blockIdx.x; c0 < nchunks; c0 += G * U) {
+  const int G = workers;
+  for (int c0 = wrank; c0 < nchunks; c0 += G * U) {
     if ((int)threadIdx.x < U) {
       const int c = c0 + (int)threadIdx.x * G;
       if (c < nchunks) ptx::spin_until_ge(ctrs + CTR_DX + (c >> 4), S);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && c0 == (int)blockIdx.x) stamp(g, 14);
+    if (threadIdx.x == 0 && c0 == wrank) stamp(g, 14);
     float4 t[U][SMAX];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -279,9 +282,10 @@ __device__ __forceinline__ void reduce_dx(const Args& g, const int* ctrs) {
   }
 }
 
-// TPR threads per loss row, NE logits per thread (C <= TPR * NE), 256 / TPR rows per CTA pass.
-template <int TPR, int NE>
-__global__ void __maxnreg__(HF_MAX_REGS)
+// TPR threads per loss row, NE logits per thread (C <= TPR * NE), 256 / TPR rows per CTA pass.  REGS: register cap
+// (HF_MAX_REGS, or 128 for data-parallel runs: IIF_HEAD_LOW_REGS leaves room for two all-reduce lanes on every SM).
+template <int TPR, int NE, int REGS>
+__global__ void __maxnreg__(REGS)
 head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmP,
                   const __grid_constant__ CUtensorMap tmDW, const __grid_constant__ Args g) {
@@ -674,9 +678,20 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   // ============================ phase R ============================
   if (g.dx.items > 0) {
-    if (g.dx.splits <= 2) reduce_dx<4, 2>(g, ctrs);
-    else if (g.dx.splits <= 4) reduce_dx<2, 4>(g, ctrs);
-    else reduce_dx<1, 8>(g, ctrs);
+    // workers: the CTAs with fewer than ceil(nB / grid) backward items (see reduce_dx)
+    const int G = (int)gridDim.x, c = (int)blockIdx.x;
+    const int max_b = (nB + G - 1) / G, rem = nB - (max_b - 1) * G;      // `rem` CTAs ran max_b items
+    int wrank = c, workers = G;
+    if (rem < G && 3 * (G - rem) >= G) {               // (a handful of idle CTAs cannot carry the whole reduce)
+      workers = G - rem;
+      if ((max_b - 1) & 1) wrank = c < G - rem ? c : -1;                  // odd last round: dealt from the top down
+      else wrank = c >= rem ? c - rem : -1;
+    }
+    if (wrank >= 0) {
+      if (g.dx.splits <= 2) reduce_dx<8, 2>(g, ctrs, wrank, workers);
+      else if (g.dx.splits <= 4) reduce_dx<4, 4>(g, ctrs, wrank, workers);
+      else reduce_dx<2, 8>(g, ctrs, wrank, workers);
+    }
   }
   if (threadIdx.x == 0) { stamp(g, 10); stamp(g, 11); }
 }
@@ -770,10 +785,15 @@ static bool make_plan(int64_t B, int64_t D, int64_t C, bool need_dx, int sms, Pl
 
 static long long* g_dbg = nullptr;
 
-template <int TPR, int NE>
-static const void* kernel_ptr() { return reinterpret_cast<const void*>(&head_fused_kernel<TPR, NE>); }
+template <int TPR, int NE, int REGS = HF_MAX_REGS>
+static const void* kernel_ptr() { return reinterpret_cast<const void*>(&head_fused_kernel<TPR, NE, REGS>); }
 
-static const void* pick_kernel(const Plan& p) {
+static const void* pick_kernel(const Plan& p, bool low_regs) {
+  if (low_regs) {
+    if (p.tpr == 128) return kernel_ptr<128, 8, 128>();
+    if (p.ne == 8) return kernel_ptr<256, 8, 128>();
+    return kernel_ptr<256, 16, 128>();
+  }
   if (p.tpr == 128) return kernel_ptr<128, 8>();
   if (p.ne == 8) return kernel_ptr<256, 8>();
   return kernel_ptr<256, 16>();
@@ -786,7 +806,8 @@ static int device_sms() {
   if (!sms[dev]) {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    for (const void* fn : {kernel_ptr<128, 8>(), kernel_ptr<256, 8>(), kernel_ptr<256, 16>()}) {
+    for (const void* fn : {kernel_ptr<128, 8>(), kernel_ptr<256, 8>(), kernel_ptr<256, 16>(), kernel_ptr<128, 8, 128>(),
+                           kernel_ptr<256, 8, 128>(), kernel_ptr<256, 16, 128>()}) {
       if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return 0;
       cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
@@ -874,7 +895,7 @@ int head_fused_launch(const iif_head_args* h, void* stream, bool dry_run) {
   cfg.dynamicSmemBytes = hf::SMEM_BYTES;
   cfg.stream = (cudaStream_t)stream;
   void* kargs[6] = {&mx, &mw, &mdz, &mp, &mdw, &g};
-  const cudaError_t e = launch_cooperative(cfg, hf::pick_kernel(p), kargs, true);
+  const cudaError_t e = launch_cooperative(cfg, hf::pick_kernel(p, (h->flags & IIF_HEAD_LOW_REGS) != 0), kargs, true);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return e == cudaSuccess ? IIF_OK : (int)e;
 }

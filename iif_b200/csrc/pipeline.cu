@@ -87,6 +87,12 @@ extern "C" int iif_pipeline_set_allreduce(iif_pipeline* p, void* const* peer_buf
   for (int i = 0; i < p->nslots; ++i) p->slots[i].ar_offset = slot_offsets_elems[i];
   p->ar_lanes = num_lanes; p->ar_next = 0;
   p->ar_on = world > 1;
+  // two (or more) all-reduces in flight need their CTAs AND the step's CTA on every SM at once: that fits with
+  // 128-thread all-reduce CTAs next to the 128-register build of the step kernel (see allreduce.cu)
+  for (int i = 0; i < p->nslots; ++i) {
+    if (p->ar_on && num_lanes > 1 && num_threads > 0 && num_threads <= 128) p->slots[i].a.flags |= IIF_HEAD_LOW_REGS;
+    else p->slots[i].a.flags &= ~IIF_HEAD_LOW_REGS;
+  }
   return IIF_OK;
 }
 

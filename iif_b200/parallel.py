@@ -101,7 +101,7 @@ class PeerAllReduce:
         self.nbuf = int(nbuf)
         self._lib = _lib.load()
         self._check = _lib.check
-        self.num_ctas = int(num_ctas) if num_ctas else 16
+        self.num_ctas = int(num_ctas) if num_ctas else 148     # one light CTA per SM, next to the step kernel's CTA
         self.num_threads = int(num_threads) if num_threads else 256
         if self.num_threads > 256 or self.num_threads % 32:
             raise ValueError("PeerAllReduce: num_threads must be a multiple of 32, at most 256 (a larger CTA needs an SM "

@@ -366,6 +366,8 @@ typedef struct iif_head_args {
  * seg/.../bbox_head.py:118 + :269-274 + autograd). */
 #define IIF_HEAD_NO_FUSED_LOSS 1      /* keep the loss rows in their own launch (3 launches per step) */
 #define IIF_HEAD_NO_PERSISTENT 2      /* do not use the one-launch persistent step (csrc/head_fused.cu) */
+#define IIF_HEAD_LOW_REGS 4           /* the 128-register build of the one-launch step: room for TWO all-reduce lanes of
+                                         128-thread CTAs on every SM next to it (set by iif_pipeline_set_allreduce) */
 IIF_API int iif_head_fwd_bwd_bf16(const iif_head_args* args, void* stream);
 /* The loss rows + AddmmBackward in ONE launch: every CTA of the backward launch first computes its share
  * of the softmax-CE rows (reads args->z, writes loss_i / dz_bf16 / argmax / rank), the grid meets at a

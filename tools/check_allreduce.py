@@ -44,6 +44,24 @@ for mc, nct, nth in CFG:
         if rank == 0:
             print(f"multicast={par.multicast} buf {i}: max rel err vs NCCL {err:.2e}; identical on all ranks: {same}")
         ok = ok and err < 1e-6 and same
+    # stress: many back-to-back calls on fresh data, every one compared with NCCL (a missing fence shows up here)
+    bad = 0
+    for it in range(60):
+        i = it % 4
+        src = torch.randn(numel, generator=g).to(dev)
+        par.buffer(i).copy_(src)
+        ref = src.clone()
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        ref /= world
+        par.all_reduce(i, st)
+        par.all_reduce((i + 1) % 4, st)          # a second one right behind it (other buffer: values checked next round)
+        out = par.buffer(i)
+        bad += int(float((out - ref).abs().max() / ref.abs().max()) > 1e-6)
+    tb = torch.tensor([bad], device=dev)
+    dist.all_reduce(tb)
+    if rank == 0:
+        print(f"  stress: {int(tb)} mismatching calls of {60 * world}")
+    ok = ok and int(tb) == 0
     # device time, back to back (each call is a cross-rank rendezvous, so this is the collective's latency)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for fn, name in ((lambda i: par.all_reduce(i % 4, st), f"peer kernel multicast={par.multicast} ctas={nct} threads={nth}"),
@@ -72,7 +90,7 @@ for mc, nct, nth in CFG:
     t0 = t[:, 0].min()
     if rank == 0:
         print("    rank0 timeline (us, median over CTAs): " + "  ".join(
-            f"{n} {np.median(t[:, i] - t0) / 1e3:.1f}" for i, n in enumerate(["start", "handshake", "data", "end"])))
+            f"{n} {np.median(t[:, i] - t0) / 1e3:.1f}" for i, n in enumerate(["start", "open", "reduced", "mid", "pulled", "end"]) if (t[:, i] > 0).any()))
     del par
 if rank == 0:
     print("ALLREDUCE CHECK", "OK" if ok else "FAILED")

@@ -6,13 +6,25 @@ N=${1:-2}; shift
 mkdir -p gpurun_out
 export IIF_B200_PEER_TIMEOUT_S=20
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-AR_SWEEP=1 timeout 300 $RUN tools/check_allreduce.py > gpurun_out/check_allreduce_n$N.log 2>&1; echo "check_allreduce exit $?"
+[ "$N" = "2" ] && export AR_SWEEP=1
+if [ "$SKIP_CHECK" != "1" ]; then
+timeout 300 $RUN tools/check_allreduce.py > gpurun_out/check_allreduce_n$N.log 2>&1; echo "check_allreduce exit $?"
 grep -vE "^\*|OMP_NUM" gpurun_out/check_allreduce_n$N.log | tail -40
+fi
 i=0
 for v in "$@"; do
   i=$((i+1))
   echo "== N=$N bench $v"
-  timeout 400 $RUN bench.py --gpus $N $v > gpurun_out/bench_n${N}_$i.log 2>&1
+  algo=auto
+  fence=gpu
+  case "$v" in push:*) algo=push; v="${v#push:}";; esac
+  case "$v" in pull:*) algo=pull; v="${v#pull:}";; esac
+  np=$N
+  case "$v" in n4:*) np=4; v="${v#n4:}";; esac
+  case "$v" in n2:*) np=2; v="${v#n2:}";; esac
+  RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port 29511"
+  case "$v" in sysfence:*) fence=sys; v="${v#sysfence:}";; esac
+  IIF_B200_AR_MIDFENCE=$fence IIF_B200_AR_ALGO=$algo timeout 400 $RUN bench.py --gpus $np $v > gpurun_out/bench_n${N}_$i.log 2>&1
   echo "exit $?"
   grep -E "^\{" gpurun_out/bench_n${N}_$i.log | python -c "
 import json,sys
