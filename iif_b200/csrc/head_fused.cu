@@ -775,6 +775,15 @@ static bool make_plan(int64_t B, int64_t D, int64_t C, bool need_dx, int sms, Pl
   else { pl.tpr = 256; pl.ne = 16; }
   const int rpb = 256 / pl.tpr;
   pl.row_blocks = (int)((B + rpb - 1) / rpb);
+  // Each CTA walks its loss rows one pass after another (~3 us a pass: an L2 round trip + two block reductions), while
+  // the multi-launch chain spreads the rows over several resident CTAs per SM.  Measured on the LVIS head: 7 passes
+  // (1024 x 1204) 50.9 us in one launch against 44.5 us as a chain, 14 passes 87.9 us -- so past a few passes the
+  // shape goes to the chain.  IIF_B200_FUSED_MAX_ROW_PASSES overrides (0 = no limit).
+  {
+    int max_passes = 4;
+    if (const char* e = getenv("IIF_B200_FUSED_MAX_ROW_PASSES")) max_passes = atoi(e);
+    if (max_passes > 0 && (pl.row_blocks + G - 1) / G > max_passes) return false;
+  }
   const int most = std::max(std::max(pl.f.items, pl.dx.items + pl.dw.items), pl.row_blocks);
   pl.grid = std::min(G, most);
   pl.part_bytes = (size_t)std::max(pl.f.items, pl.dx.items) * TM * TN * 4;

@@ -101,7 +101,10 @@ class PeerAllReduce:
         self.nbuf = int(nbuf)
         self._lib = _lib.load()
         self._check = _lib.check
-        self.num_ctas = int(num_ctas) if num_ctas else 148     # one light CTA per SM, next to the step kernel's CTA
+        # measured on one 8 x B200 box (profiles/r2_multigpu.md): 2 GPUs -> the pull form, one CTA per SM (28 us alone,
+        # 33 us/step overlapped); 4+ GPUs -> the push form with in-switch reduction, where FEWER CTAs interfere less
+        # with the step they overlap (8 GPUs: 16 CTAs 39.8 us/step, 48 CTAs 44.7, 148 CTAs 45.0)
+        self.num_ctas = int(num_ctas) if num_ctas else (148 if self.world <= 2 else 16)
         self.num_threads = int(num_threads) if num_threads else 256
         if self.num_threads > 256 or self.num_threads % 32:
             raise ValueError("PeerAllReduce: num_threads must be a multiple of 32, at most 256 (a larger CTA needs an SM "

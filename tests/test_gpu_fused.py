@@ -10,6 +10,13 @@ from oracle import head_oracle as ho
 from _common import TOL_BF16, rel_err, head_inputs, iif_row, bf16_round
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _one_launch_for_every_shape(monkeypatch):
+    """The library routes many-rows-per-CTA shapes (LVIS) to the multi-launch chain for speed; parity of the
+    one-launch step is tested on them all the same."""
+    monkeypatch.setenv("IIF_B200_FUSED_MAX_ROW_PASSES", "0")
 DEV = "cuda:0"
 BF = torch.bfloat16
 
