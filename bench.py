@@ -776,6 +776,36 @@ def main():
     e2e = {"value": world * B * n_e2e / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * D * 2 + B * 8,
            "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e, "loss_read_lag_steps": lag,
            "api": e2e_api, "last_loss": e2e_loss[0], "modes": e2e_alt}
+    if world == 1:
+        # What bounds e2e on THIS box (diagnostic, outside the timed regions): the host's time inside the two API calls
+        # of a staged step, and the PCIe copy of one batch alone (pinned host -> device, back to back, CUDA events).
+        staged = True
+        t_sub = t_wait = 0.0
+        e2e_run(2 * S)
+        fence()
+        for i in range(n_e2e):
+            k = i % S
+            ta = time.perf_counter()
+            if i >= lag:
+                pipe.wait((i - lag) % S)
+            tb = time.perf_counter()
+            pipe.submit_staged(k)
+            tc = time.perf_counter()
+            t_wait += tb - ta
+            t_sub += tc - tb
+        pipe.sync()
+        fence()
+        dst = torch.empty_like(hx[0], device=dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            dst.copy_(hx[0], non_blocking=True)
+        c0.record()
+        for i in range(50):
+            dst.copy_(hx[i % 4], non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        e2e["bound"] = {"host_us_per_step_in_submit": t_sub / n_e2e * 1e6, "host_us_per_step_in_wait": t_wait / n_e2e * 1e6,
+                        "h2d_copy_alone_us": c0.elapsed_time(c1) / 50 * 1e3, "h2d_bytes": B * D * 2}
     pipe.close()
 
     return emit_line(args, locals())

@@ -775,14 +775,20 @@ static bool make_plan(int64_t B, int64_t D, int64_t C, bool need_dx, int sms, Pl
   else { pl.tpr = 256; pl.ne = 16; }
   const int rpb = 256 / pl.tpr;
   pl.row_blocks = (int)((B + rpb - 1) / rpb);
-  // Each CTA walks its loss rows one pass after another (~3 us a pass: an L2 round trip + two block reductions), while
-  // the multi-launch chain spreads the rows over several resident CTAs per SM.  Measured on the LVIS head: 7 passes
-  // (1024 x 1204) 50.9 us in one launch against 44.5 us as a chain, 14 passes 87.9 us -- so past a few passes the
-  // shape goes to the chain.  IIF_B200_FUSED_MAX_ROW_PASSES overrides (0 = no limit).
+  // Routing between this launch and the multi-launch chain (profiles/r2_route.jsonl, us/step one launch vs chain):
+  // 256x2048x1000 23.6 / 29.2, 256x2048x365 19.2 / 29.4, 512x1024x1204 33.6 / 35.8, 512x2048x1000 33.5 / 30.5,
+  // 1024x1024x1204 51.2 / 47.7, 1024x2048x1000 52.2 / 40.0, 2048x1024x1204 88.0 / 52.3, 2048x2048x1000 92.5 / 60.5.
+  // The single launch saves the fixed costs between launches (~6 us) but runs one CTA per SM -- no neighbour CTA whose
+  // MMAs cover a drain -- and each CTA walks its loss rows one pass after another (~3 us a pass), where the chain's
+  // loss launch keeps several CTAs per SM.  So it is taken up to B*D*C = 0.8e9 multiply-adds per GEMM and 4 row passes.
+  // IIF_B200_FUSED_MAX_WORK (multiply-adds, 0 = no limit) and IIF_B200_FUSED_MAX_ROW_PASSES (0 = no limit) override.
   {
     int max_passes = 4;
+    double max_work = 0.8e9;
     if (const char* e = getenv("IIF_B200_FUSED_MAX_ROW_PASSES")) max_passes = atoi(e);
+    if (const char* e = getenv("IIF_B200_FUSED_MAX_WORK")) max_work = atof(e);
     if (max_passes > 0 && (pl.row_blocks + G - 1) / G > max_passes) return false;
+    if (max_work > 0 && (double)B * (double)D * (double)C > max_work) return false;
   }
   const int most = std::max(std::max(pl.f.items, pl.dx.items + pl.dw.items), pl.row_blocks);
   pl.grid = std::min(G, most);

@@ -2,9 +2,12 @@
 //     v = v_h + v_m + v_l,   v_h = bf16(v), v_m = bf16(v - v_h), v_l = bf16(v - v_h - v_m)
 // (8 + 8 + 8 = 24 significand bits: the split is exact up to the last bit of fp32) and a product A B^T is formed as
 // the six partial products whose terms carry at least 2^-24 of the result,
-//     A B^T  ~=  A_h B_h + A_h B_m + A_m B_h + A_h B_l + A_m B_m + A_l B_h,
+//     A B^T  ~=  A_l B_h + A_m B_m + A_h B_l + A_m B_h + A_h B_m + A_h B_h,
 // accumulated in fp32 by the SAME tcgen05 kernel as the bf16 mode -- as ONE GEMM whose contraction dimension is six
-// copies long: A'' = [A_h A_h A_m A_h A_m A_l], B'' = [B_h B_m B_h B_l B_m B_h] along K.  This file holds the two
+// copies long: A'' = [A_l A_m A_h A_m A_h A_h], B'' = [B_h B_m B_l B_h B_m B_h] along K -- SMALLEST terms first: an
+// unsplit accumulation chain then collects the 2^-16 and 2^-8 sized corrections before the leading products arrive
+// (largest first measured 2.1e-5 max relative error at 16384 x 2048 x 1000, where K runs unsplit, against 2.9e-6 at
+// 256 rows).  This file holds the two
 // operand-expansion kernels (K along the columns of a row-major matrix / K along its rows).  Replaces the FFMA sgemm
 // (gemm_f32.cu) as the 1e-5 parity path of nn.Linear (cls/resnet_pytorch.py:219,293; bbox_head.py:118) when selected.
 #include "common.cuh"
@@ -23,8 +26,8 @@ __device__ __forceinline__ void split3(float v, uint16_t& h, uint16_t& m, uint16
 }
 
 // which term (0 = h, 1 = m, 2 = l) the k-th of the six copies holds: the A side and the B side of the product
-__constant__ int kTermA[6] = {0, 0, 1, 0, 1, 2};
-__constant__ int kTermB[6] = {0, 1, 0, 2, 1, 0};
+__constant__ int kTermA[6] = {2, 1, 0, 1, 0, 0};
+__constant__ int kTermB[6] = {0, 1, 2, 0, 1, 0};
 
 // K along the COLUMNS: in [rows, cols] fp32 -> out [rows, 6 * cols_pad] bf16, copy k at columns [k * cols_pad, ..)
 // (cols_pad = cols rounded up to 8 so that every copy starts 16-byte aligned; the padding is zero)

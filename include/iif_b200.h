@@ -273,9 +273,9 @@ IIF_API int iif_linear_fwd_f32(const float* x, int64_t ldx, const float* w, int6
                        int64_t B, int64_t D, int64_t C, void* stream);
 
 /* fp32 parity mode on the tensor cores: expand an fp32 operand into six bf16 copies along the contraction dimension
- * (v = v_h + v_m + v_l; A side: h h m h m l, B side: h m h l m h) so that ONE call of the bf16 GEMM entry points above /
- * below with a six times longer K forms  A_h B_h + A_h B_m + A_m B_h + A_h B_l + A_m B_m + A_l B_h  in fp32 -- the
- * product to ~2^-24 relative, i.e. within the 1e-5 bar, at tensor-core speed (csrc/split3.cu).
+ * (v = v_h + v_m + v_l; A side: l m h m h h, B side: h m l h m h) so that ONE call of the bf16 GEMM entry points above /
+ * below with a six times longer K forms  A_l B_h + A_m B_m + A_h B_l + A_m B_h + A_h B_m + A_h B_h  in fp32 (smallest
+ * terms first) -- the product to ~2^-24 relative, i.e. within the 1e-5 bar, at tensor-core speed (csrc/split3.cu).
  *   k_along_rows = 0: in [rows, cols] -> out [rows, 6 * pad8(cols)] (copy k at column k * pad8(cols); padding zero)
  *   k_along_rows = 1: in [rows, cols] -> out [6 * pad8(rows), cols] (copy k at row k * pad8(rows); padding zero)
  *   side_b: 0 = the A operand's term order, 1 = the B operand's. */

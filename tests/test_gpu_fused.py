@@ -17,6 +17,7 @@ def _one_launch_for_every_shape(monkeypatch):
     """The library routes many-rows-per-CTA shapes (LVIS) to the multi-launch chain for speed; parity of the
     one-launch step is tested on them all the same."""
     monkeypatch.setenv("IIF_B200_FUSED_MAX_ROW_PASSES", "0")
+    monkeypatch.setenv("IIF_B200_FUSED_MAX_WORK", "0")
 DEV = "cuda:0"
 BF = torch.bfloat16
 
@@ -152,3 +153,42 @@ def test_fused_step_in_cuda_graph():
         g.replay()
     torch.cuda.synchronize()
     assert float(hs.loss) == ref[0] and torch.equal(hs.dw, ref[1]) and torch.equal(hs.dx, ref[2])
+
+
+@pytest.mark.parametrize("B,D,C", [(65536, 2048, 1000), (16384, 512, 10000)])
+def test_head_step_full_size_sampled_rows(B, D, C):
+    """BASELINE.json's sweep sizes through the one C-ABI call (the multi-launch chain at these sizes): sampled rows of
+    Z / dZ / dX and sampled classes of dW / db against the float64 oracle, plus whole-array identities on the step's own
+    outputs (db = column sums of dZ, rows of dZ / iif sum to ~0, loss = sum of the per-row losses)."""
+    from iif_b200.ops import HeadStep
+    g = torch.Generator(device="cpu").manual_seed(B + C)
+    counts = np.maximum((1280 * 0.01 ** (np.arange(C) / (C - 1.0))).astype(np.int64), 1)
+    iif = iif_row(counts, "smooth")
+    x = torch.randn(B, D, generator=g).to(DEV).to(BF)
+    w = ((torch.rand(C, D, generator=g) * 2 - 1) / D ** 0.5).to(DEV).to(BF)
+    b = torch.full((C,), 0.01, device=DEV)
+    y = torch.multinomial(torch.from_numpy(counts / counts.sum()), B, replacement=True, generator=g).to(DEV)
+    hs = HeadStep(B, D, C, DEV, dx_bf16=False, want_acc=True)
+    hs.bind(x, w, b, T(iif).reshape(-1), y)
+    loss = hs.launch()
+    torch.cuda.synchronize()
+    rows = np.unique(np.concatenate([[0, 127, 128, B - 1], np.random.default_rng(3).integers(0, B, 60)]))
+    xr, wn, yn = N(x[rows]).astype(np.float64), N(w).astype(np.float64), y.cpu().numpy()
+    ref = ho.head_fwd_bwd(xr, wn, N(b), iif, yn[rows], scale=1.0 / B)
+    assert rel_err(N(hs.z[rows]), ref["z"]) < 2e-5
+    assert rel_err(N(hs.dz[rows, :C]), ref["dz"]) < 6e-3            # bf16 storage of dZ
+    assert rel_err(N(hs.dx[rows]), ref["dz"] @ wn) < 6e-3
+    assert rel_err(N(hs.loss_i[rows]), ref["loss_i"] / B) < 1e-4
+    assert np.array_equal(hs.argmax[rows].cpu().numpy(), ho.argmax_first(N(hs.z[rows])))
+    assert np.array_equal(hs.rank[rows].cpu().numpy(), ho.label_rank(N(hs.z[rows]), yn[rows]))
+    # whole-array identities on the step's own outputs
+    dz = hs.dz[:, :C].float()
+    assert float(loss) == pytest.approx(float(hs.loss_i.double().sum()), rel=1e-5)
+    assert rel_err(N(hs.db), N(dz.double().sum(0))) < 2e-3
+    unscaled = dz.double() / T(iif).reshape(1, -1).double()         # dZ_c = iif_c (p_c - [c = y]) / B
+    assert float(unscaled.sum(1).abs().max()) < 0.05 / B            # rows of p - onehot sum to 0 up to bf16 rounding
+    cls = np.unique(np.concatenate([[0, 127, 128, C - 1], np.random.default_rng(4).integers(0, C, 28)]))
+    dw_ref = dz[:, cls].double().T @ x.double()                     # the kernel's own bf16 dZ, fp64 accumulation
+    assert rel_err(N(hs.dw[cls]), dw_ref.cpu().numpy()) < 2e-3
+    r = hs.rank.cpu().numpy()
+    assert hs.acc_counts.cpu().tolist() == [int((r < 1).sum()), int((r < 5).sum())]

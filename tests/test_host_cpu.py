@@ -128,3 +128,25 @@ def test_bench_reads_committed_ncu_traffic():
     assert bench.ncu_traffic("loss_linear_bwd_bf16", (512, 2048, 1000)) == (None, None)
     p = bench.peaks()
     assert p["hbm"] > 1000 and p["tf_burst"] >= p["tf_sust"] > 100
+    t2, src2 = bench.ncu_traffic("head_step_fused_bf16", (256, 2048, 1000))
+    assert t2 is not None and 4e6 < t2 < 2e7 and "r2_ncu_head_full_summary" in src2
+
+
+def test_one_launch_step_routing(monkeypatch):
+    """Host-only plan of the one-launch step (iif_debug_fused_plan): the head shapes of BASELINE.json qualify, shapes
+    with more work per CTA go to the multi-launch chain (IIF_EUNSUPPORTED = -3), the environment overrides lift the
+    limits, and the hard limits (B <= 2048, C <= 4096) stay."""
+    from iif_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_int * 12)()
+    plan = lambda B, D, C: lib.iif_debug_fused_plan(B, D, C, 1, 148, out)
+    for shape in [(256, 2048, 1000), (256, 2048, 365), (128, 64, 10), (512, 1024, 1204), (1, 8, 1)]:
+        assert plan(*shape) == 0, shape
+    assert plan(256, 2048, 1000) == 0 and list(out)[:6] == [148, 8, 128, 2, 64, 128]
+    for shape in [(1024, 1024, 1204), (2048, 1024, 1204), (512, 2048, 1000), (2048, 2048, 1000)]:
+        assert plan(*shape) == -3, shape
+    monkeypatch.setenv("IIF_B200_FUSED_MAX_ROW_PASSES", "0")
+    monkeypatch.setenv("IIF_B200_FUSED_MAX_WORK", "0")
+    for shape in [(1024, 1024, 1204), (2048, 1024, 1204), (512, 512, 4096)]:
+        assert plan(*shape) == 0, shape
+    assert plan(4096, 1024, 1204) == -3 and plan(256, 1024, 4097) == -3
