@@ -503,7 +503,7 @@ def main():
             peer = None
             ar_kind = "nccl (peer-memory all-reduce unavailable on this box)"
         else:
-            ar_kind = "peer-memory kernel" + (" (NVLS multimem)" if peer.multicast else " (peer loads/stores)")
+            ar_kind = f"peer-memory kernel ({peer.form})"
             ar_kind += f", {peer.num_ctas}x{peer.num_threads} threads, {peer.lanes} in flight"
     shared_ws = torch.zeros(max(int(ops._lib.load().iif_gemm_ws_bytes(B, D, C)), 1), dtype=torch.uint8, device=dev)
     for s in range(S):

@@ -317,7 +317,7 @@ extern "C" int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* p
   if (lane < 0 || lane >= AR_LANES) return IIF_EINVAL;
   if (n_elems < 0 || offset_elems < 0 || (n_elems & 3) || (offset_elems & 3)) return IIF_EALIGN;
   if (n_elems == 0) return IIF_OK;
-  if (num_ctas <= 0) num_ctas = world <= 2 ? kNumSMs : 16;   // (measured: see iif_b200/parallel.py)
+  if (num_ctas <= 0) num_ctas = world <= 2 ? kNumSMs : (world < 8 ? 48 : 16);   // (measured: see iif_b200/parallel.py)
   if (num_ctas > AR_MAX_CTAS) num_ctas = AR_MAX_CTAS;
   if (num_threads <= 0) num_threads = 256;
   if (num_threads > AR_THREADS || (num_threads & 31) || num_threads < 32) return IIF_EINVAL;

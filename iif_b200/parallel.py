@@ -17,6 +17,7 @@ from __future__ import annotations
 from typing import Optional, Tuple
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -103,8 +104,9 @@ class PeerAllReduce:
         self._check = _lib.check
         # measured on one 8 x B200 box (profiles/r2_multigpu.md): 2 GPUs -> the pull form, one CTA per SM (28 us alone,
         # 33 us/step overlapped); 4+ GPUs -> the push form with in-switch reduction, where FEWER CTAs interfere less
-        # with the step they overlap (8 GPUs: 16 CTAs 39.8 us/step, 48 CTAs 44.7, 148 CTAs 45.0)
-        self.num_ctas = int(num_ctas) if num_ctas else (148 if self.world <= 2 else 16)
+        # with the step they overlap (8 GPUs: 16 CTAs 39.8 us/step, 48 CTAs 44.7, 148 CTAs 45.0; 4 GPUs, where a rank's
+        # slice is twice as long: 16 CTAs 43.8, 48 CTAs 41.1, 148 CTAs 49.1)
+        self.num_ctas = int(num_ctas) if num_ctas else (148 if self.world <= 2 else (48 if self.world < 8 else 16))
         self.num_threads = int(num_threads) if num_threads else 256
         if self.num_threads > 256 or self.num_threads % 32:
             raise ValueError("PeerAllReduce: num_threads must be a multiple of 32, at most 256 (a larger CTA needs an SM "
@@ -131,6 +133,17 @@ class PeerAllReduce:
         self._mc = C.c_void_p(mc if self.multicast else 0)
         self._bufs = C.c_void_p(int(self.hdl.buffer_ptrs_dev))
         self._flags = C.c_void_p(int(self.fhdl.buffer_ptrs_dev))
+
+    @property
+    def form(self) -> str:
+        """Which kernel iif_allreduce_mean_f32 picks (same rule as csrc/allreduce.cu; IIF_B200_AR_ALGO overrides)."""
+        env = os.environ.get("IIF_B200_AR_ALGO", "")[:3]
+        pull = env == "pul" or (env != "pus" and (self.world <= 2 or not self.multicast))
+        if pull:
+            how = "in-switch multimem reduce" if (self.multicast and self.world >= 4) else "peer loads"
+            return f"pull form: local slice reduced with {how}, gathered with peer loads"
+        return ("push form: in-switch multimem.ld_reduce + multimem.st broadcast" if self.multicast
+                else "push form: peer loads + remote stores")
 
     def buffer(self, i: int) -> torch.Tensor:
         return self.mem[i * self.stride: i * self.stride + self.numel]
