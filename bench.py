@@ -11,7 +11,9 @@ every rank processes its own B rows (weak scaling, row sharding) and the head's 
 NVLink kernel on side streams, overlapping the next steps' compute (`--allreduce nccl` = the NCCL arm).
 
 `e2e`: the same step through the host-batch API (`ops.HeadPipeline`): features + labels copied from
-pinned host memory and the loss brought back to the host every step.
+pinned host memory and the loss brought back to the host every step; wall clock, median of five ~30 ms
+regions after a warm-up of the host-batch path (`e2e.bound`: every region, host time per API call, the
+batch's H2D copy alone).
 
 Timing hygiene: the step rotates through S independent sets of inputs AND outputs whose combined
 footprint exceeds the 126 MB L2, so no step finds its operands in L2 (config.l2 says so); CUDA
