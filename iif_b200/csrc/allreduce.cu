@@ -317,7 +317,14 @@ extern "C" int iif_allreduce_mean_f32(void* const* peer_bufs_dev, void* const* p
   if (lane < 0 || lane >= AR_LANES) return IIF_EINVAL;
   if (n_elems < 0 || offset_elems < 0 || (n_elems & 3) || (offset_elems & 3)) return IIF_EALIGN;
   if (n_elems == 0) return IIF_OK;
-  if (num_ctas <= 0) num_ctas = world <= 2 ? kNumSMs : (world < 8 ? 48 : 16);   // (measured: see iif_b200/parallel.py)
+  {
+    // default geometry by form (measured: see iif_b200/parallel.py): the pull form wants a CTA per SM, the push form
+    // with in-switch reduction few CTAs
+    const char* e = getenv("IIF_B200_AR_ALGO");
+    const bool want_pull = (e && e[0] == 'p' && e[1] == 'u' && e[2] == 'l') ||
+                           (!(e && e[0] == 'p' && e[1] == 'u' && e[2] == 's') && (world <= 2 || !multicast_ptr));
+    if (num_ctas <= 0) num_ctas = want_pull ? kNumSMs : (world < 8 ? 48 : 16);
+  }
   if (num_ctas > AR_MAX_CTAS) num_ctas = AR_MAX_CTAS;
   if (num_threads <= 0) num_threads = 256;
   if (num_threads > AR_THREADS || (num_threads & 31) || num_threads < 32) return IIF_EINVAL;

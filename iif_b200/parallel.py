@@ -106,16 +106,11 @@ class PeerAllReduce:
         # 33 us/step overlapped); 4+ GPUs -> the push form with in-switch reduction, where FEWER CTAs interfere less
         # with the step they overlap (8 GPUs: 16 CTAs 39.8 us/step, 48 CTAs 44.7, 148 CTAs 45.0; 4 GPUs, where a rank's
         # slice is twice as long: 16 CTAs 43.8, 48 CTAs 41.1, 148 CTAs 49.1)
-        self.num_ctas = int(num_ctas) if num_ctas else (148 if self.world <= 2 else (48 if self.world < 8 else 16))
         self.num_threads = int(num_threads) if num_threads else 256
         if self.num_threads > 256 or self.num_threads % 32:
             raise ValueError("PeerAllReduce: num_threads must be a multiple of 32, at most 256 (a larger CTA needs an SM "
                              "to itself and can dead-lock against the GEMM launches it overlaps)")
-        # The all-reduce overlaps the next step's GEMM launches and blocks on other GPUs: keep its footprint
-        # out of the resident-CTA budget their in-kernel rendezvous rely on (include/iif_b200.h).
         self.lanes = max(1, min(int(lanes), 4))     # all-reduces of consecutive steps that may be in flight at once
-        self._check(self._lib.iif_gemm_reserve_slots(self.lanes * self.num_ctas),
-                    "gemm_reserve_slots")
         try:
             self.mem = symm_mem.empty(self.nbuf * self.stride, dtype=torch.float32, device=self.device)
             self.mem.zero_()
@@ -133,6 +128,12 @@ class PeerAllReduce:
         self._mc = C.c_void_p(mc if self.multicast else 0)
         self._bufs = C.c_void_p(int(self.hdl.buffer_ptrs_dev))
         self._flags = C.c_void_p(int(self.fhdl.buffer_ptrs_dev))
+        pull = self.form.startswith("pull")
+        self.num_ctas = int(num_ctas) if num_ctas else (148 if pull else (48 if self.world < 8 else 16))
+        # The all-reduce overlaps the next step's GEMM launches and blocks on other GPUs: keep its footprint
+        # out of the resident-CTA budget their in-kernel rendezvous rely on (include/iif_b200.h).
+        self._check(self._lib.iif_gemm_reserve_slots(self.lanes * self.num_ctas),
+                    "gemm_reserve_slots")
 
     @property
     def form(self) -> str:
