@@ -201,8 +201,11 @@ def run_reference(args, B, D, C):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": max(3, min(args.warmup, 20)), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "B_per_gpu": B, "D": D, "C": C,
-                       "note": "CPU arm: one process on the host cores, not sharded over GPUs"},
+            "config": {"workload": WORKLOAD if (B, D, C) == (256, 2048, 1000) else f"IIF head {B}x{D}x{C}",
+                       "loss": "softmax", "B_per_gpu": B, "D": D, "C": C, "global_batch": B * max(args.gpus, 1),
+                       "variant": args.variant, "parallelism": f"dp{max(args.gpus, 1)}",
+                       "note": "CPU arm: one process on the host cores times a bounded sample (one rank's batch per step) "
+                               "of the workload, not sharded over GPUs"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "repeats": repeats}
