@@ -150,3 +150,34 @@ def test_one_launch_step_routing(monkeypatch):
     for shape in [(1024, 1024, 1204), (2048, 1024, 1204), (512, 512, 4096)]:
         assert plan(*shape) == 0, shape
     assert plan(4096, 1024, 1204) == -3 and plan(256, 1024, 4097) == -3
+
+
+def test_one_launch_plan_fuzz(monkeypatch):
+    """The host-side planner of the one-launch step over random shapes / SM counts (routing limits lifted): it either
+    declines (IIF_EUNSUPPORTED) or returns a plan whose grid fits the device, whose split counts are within the
+    kernel's bounds and whose loss-row geometry covers the class count."""
+    import random
+    from iif_b200 import _lib
+    monkeypatch.setenv("IIF_B200_FUSED_MAX_ROW_PASSES", "0")
+    monkeypatch.setenv("IIF_B200_FUSED_MAX_WORK", "0")
+    lib = _lib.load()
+    out = (ctypes.c_int * 12)()
+    rnd = random.Random(7)
+    accepted = 0
+    for _ in range(3000):
+        B = rnd.choice([1, 2, 7, 128, 129, 256, 777, 1024, 2048, 2049, rnd.randint(1, 3000)])
+        D = rnd.choice([1, 8, 63, 64, 65, 520, 1024, 2048, 8192, rnd.randint(1, 20000)])
+        C = rnd.choice([1, 10, 128, 129, 365, 1000, 1203, 1204, 4096, 4097, rnd.randint(1, 5000)])
+        sms = rnd.choice([148, 132, 64, 16, 1])
+        need_dx = rnd.randint(0, 1)
+        rc = lib.iif_debug_fused_plan(B, D, C, need_dx, sms, out)
+        assert rc in (0, -3), (rc, B, D, C)
+        if B > 2048 or C > 4096:
+            assert rc == -3
+        if rc == 0:
+            accepted += 1
+            grid, f_splits, f_items, dx_splits, dx_items, dw_items, _, tpr, ne, row_blocks = list(out)[:10]
+            assert 1 <= grid <= sms and 1 <= f_splits <= 8 and f_items >= 1 and dw_items >= 1 and row_blocks >= 1
+            assert (dx_items == 0) if not need_dx else (1 <= dx_splits <= 8 and dx_items >= 1)
+            assert tpr in (128, 256) and ne in (8, 16) and tpr * ne >= C
+    assert accepted > 1500
